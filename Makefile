@@ -1,0 +1,25 @@
+# Build the sm_100a shared library (C ABI in include/loftr_b200.h) and the test helpers.
+NVCC      ?= nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
+LIB       := loftr_b200/lib/libloftr_b200.so
+CSRC      := loftr_b200/csrc
+HDRS      := $(wildcard $(CSRC)/*.cuh) include/loftr_b200.h
+
+all: $(LIB) build/bringup oracle
+
+$(LIB): $(CSRC)/engine.cu $(HDRS)
+	@mkdir -p loftr_b200/lib
+	$(NVCC) $(NVFLAGS) -shared $(CSRC)/engine.cu -o $@
+
+build/bringup: tests/cuda/bringup.cu $(LIB)
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O2 -std=c++17 tests/cuda/bringup.cu -o $@ -Lloftr_b200/lib -lloftr_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../loftr_b200/lib'
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -rf build loftr_b200/lib oracle/_build
+
+.PHONY: all oracle clean

@@ -1,0 +1,175 @@
+/*
+ * loftr_b200 -- C ABI of the B200-native LoFTR matching hot path.
+ *
+ * Every entry point replaces one `forward` of the reference (zju3dv/LoFTR, paths relative to the
+ * reference root) and is what a binding from the reference side would call:
+ *
+ *   lb_coarse_prep            <- PositionEncodingSine.forward + rearrange   src/loftr/utils/position_encoding.py:37-42,
+ *                                                                           src/loftr/loftr.py:58-59
+ *   lb_transformer_forward    <- LocalFeatureTransformer.forward            src/loftr/loftr_module/transformer.py:80-101
+ *                                (LoFTREncoderLayer.forward :35-58, LinearAttention.forward linear_attention.py:20-47)
+ *   lb_coarse_match           <- CoarseMatching.forward + get_coarse_match  src/loftr/utils/coarse_matching.py:87-148,150-261
+ *                                (Sinkhorn branch: log_optimal_transport, third_party/SuperGluePretrainedNetwork/
+ *                                 models/superglue.py:141-170)
+ *   lb_fine_preprocess        <- FinePreprocess.forward                     src/loftr/loftr_module/fine_preprocess.py:29-59
+ *   lb_fine_match             <- FineMatching.forward + get_fine_match      src/loftr/utils/fine_matching.py:15-74
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless a parameter says "host".  No torch / C++ types cross this
+ *     boundary; `stream` is a cudaStream_t passed as void*.
+ *   - Functions enqueue work on `stream` and return without synchronising.  Return value 0 = success,
+ *     non-zero = error (lb_last_error() gives the message for the calling thread).
+ *   - Workspaces are caller-provided; query the size with the matching *_workspace_bytes function.
+ *   - "planes": an fp32 matrix x kept as two fp16 matrices hi, lo with x ~= hi + lo.
+ *     A "cat buffer" is a [rows, 2C] pair of planes; columns [0, C) hold the token features.
+ *   - There is no CPU fallback: on a machine without an sm_100 device every compute entry point fails.
+ */
+#ifndef LOFTR_B200_H_
+#define LOFTR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LB_MATCH_DUAL_SOFTMAX 0
+#define LB_MATCH_SINKHORN 1
+#define LB_LAYER_SELF 0
+#define LB_LAYER_CROSS 1
+
+int lb_version(void);
+const char* lb_last_error(void);
+/* number of kernels this library has launched in this process (for bench.py's gpu_launches) */
+long long lb_launch_count(void);
+
+/* fp32 [rows, cols] (row stride ld_x) -> fp16 planes written at column offset col0 of [rows, ld_pl] buffers. */
+int lb_split_planes(const float* x, long rows, int cols, int ld_x, void* hi, void* lo, int ld_pl, int col0,
+                    void* stream);
+
+/* Test hook for the contraction core: out[b, m, n] = sum_k A[b, m, k] * B[b?, n, k] (fp32 out).
+ * b_batch_stride == 0 shares B across batches. */
+int lb_gemm_split(const void* a_hi, const void* a_lo, long lda, long a_batch_stride, const void* b_hi,
+                  const void* b_lo, long ldb, long b_batch_stride, float* out, long ldo, long o_batch_stride,
+                  int batches, int M, int N, int K, void* stream);
+
+/* feat [n_img, C, h, w] fp32 NCHW + pe [C, pe_h, pe_w] -> x_f32 [n_img*h*w, C], cat planes [rows, 2C] cols [0,C). */
+int lb_coarse_prep(const float* feat_nchw, const float* pe, int n_img, int C, int h, int w, int pe_h, int pe_w,
+                   float* x_f32, void* cat_hi, void* cat_lo, void* stream);
+
+/* Weights of one LoFTREncoderLayer (state_dict names in comments), as fp16 planes of the [out, in] matrices. */
+typedef struct LbEncoderLayerWeights {
+  const void* wqkv_hi; /* [3C, C]: rows = q_proj.weight, k_proj.weight, v_proj.weight */
+  const void* wqkv_lo;
+  const void* wm_hi;   /* [C, C]   merge.weight */
+  const void* wm_lo;
+  const void* w1_hi;   /* [2C, 2C] mlp.0.weight */
+  const void* w1_lo;
+  const void* w2_hi;   /* [C, 2C]  mlp.2.weight */
+  const void* w2_lo;
+  const float* ln1_g;  /* norm1.weight / bias, norm2.weight / bias  [C] */
+  const float* ln1_b;
+  const float* ln2_g;
+  const float* ln2_b;
+} LbEncoderLayerWeights;
+
+/* Token state of a LocalFeatureTransformer run over two token sets (feat0 rows first, then feat1 rows). */
+typedef struct LbTransformerState {
+  float* x_f32;         /* [rows0 + rows1, C]   in/out */
+  void* cat_hi;         /* [rows0 + rows1, 2C]  in/out (cols [0,C) = features, cols [C,2C) scratch) */
+  void* cat_lo;
+  const uint8_t* mask;  /* optional [rows0 + rows1], 1 = valid (mask0 then mask1 flattened) */
+  int n_groups;         /* images (coarse) or windows (fine) per set */
+  int group_rows0;      /* L  (or 25) */
+  int group_rows1;      /* S  (or 25) */
+} LbTransformerState;
+
+size_t lb_transformer_workspace_bytes(int d_model, int nhead, int n_groups, int group_rows0, int group_rows1);
+int lb_transformer_forward(const LbEncoderLayerWeights* layers /*host*/, const int* kinds /*host*/, int n_layers,
+                           int d_model, int nhead, const LbTransformerState* st /*host*/, void* ws,
+                           size_t ws_bytes, void* stream);
+
+typedef struct LbCoarseMatchArgs {
+  const void* f0_hi;   /* planes of feat_c0 [n_pairs*L, >=C] */
+  const void* f0_lo;
+  const void* f1_hi;   /* planes of feat_c1 [n_pairs*S, >=C] */
+  const void* f1_lo;
+  int ld;              /* row stride (elements) of the planes */
+  int n_pairs, L, S, C;
+  int h0c, w0c, h1c, w1c;
+  int match_type;      /* LB_MATCH_* */
+  float temperature;   /* dsmax_temperature */
+  float thr;
+  int border_rm;
+  const float* bin_score; /* device scalar (sinkhorn) */
+  int skh_iters;
+  int skh_prefilter;
+  const uint8_t* mask0;   /* optional [n_pairs*L] */
+  const uint8_t* mask1;   /* optional [n_pairs*S] */
+  float img_scale;        /* hw0_i[0] / hw0_c[0] */
+  const float* scale0;    /* optional [n_pairs, 2] */
+  const float* scale1;
+  long capacity;          /* entries available in the outputs below (n_pairs*L always suffices) */
+  long long* b_ids;
+  long long* i_ids;
+  long long* j_ids;
+  float* mconf;
+  float* mkpts0_c;        /* [capacity, 2] */
+  float* mkpts1_c;
+  int* count;             /* device int: number of matches M */
+} LbCoarseMatchArgs;
+
+size_t lb_coarse_match_workspace_bytes(int n_pairs, int L, int S);
+int lb_coarse_match(const LbCoarseMatchArgs* args /*host*/, void* ws, size_t ws_bytes, void* stream);
+
+typedef struct LbFinePreprocessArgs {
+  const float* feat_f0;   /* fine maps, any strides (elements): index = n*sn + c*sc + y*sh + x*sw */
+  const float* feat_f1;
+  long sn0, sc0, sh0, sw0;
+  long sn1, sc1, sh1, sw1;
+  int Hf0, Wf0, Hf1, Wf1;
+  int w0c, w1c;
+  int stride;             /* hw0_f[0] // hw0_c[0] */
+  int W;                  /* fine_window_size */
+  int Cf, Cc;             /* fine / coarse d_model */
+  const float* feat_c;    /* coarse transformer output x_f32: n_pairs*L rows then n_pairs*S rows, [.., Cc] */
+  int n_pairs, L, S;
+  long M;                 /* number of coarse matches */
+  const long long* b_ids;
+  const long long* i_ids;
+  const long long* j_ids;
+  const float* down_w;    /* fine_preprocess.down_proj.weight [Cf, Cc], bias [Cf] */
+  const float* down_b;
+  const float* merge_w;   /* fine_preprocess.merge_feat.weight [Cf, 2Cf] (fp32) */
+  const float* merge_b;
+  const void* merge_w_hi; /* planes of merge_w[:, 0:Cf]  -> [Cf, Cf] */
+  const void* merge_w_lo;
+  /* outputs: fine transformer state, rows = side*M*W*W + m*W*W + k */
+  float* x_f32;           /* [2*M*W*W, Cf] */
+  void* cat_hi;           /* [2*M*W*W, 2Cf] */
+  void* cat_lo;
+} LbFinePreprocessArgs;
+
+size_t lb_fine_preprocess_workspace_bytes(long M, int W, int Cf);
+int lb_fine_preprocess(const LbFinePreprocessArgs* args /*host*/, void* ws, size_t ws_bytes, void* stream);
+
+typedef struct LbFineMatchArgs {
+  const float* f0;        /* [M*W*W, C] fine transformer output, window side 0 */
+  const float* f1;        /* side 1 */
+  int W, C;
+  long M;
+  float img_scale;        /* hw0_i[0] / hw0_f[0] */
+  const float* scale1;    /* optional [n_pairs, 2] */
+  const long long* b_ids;
+  const float* mkpts1_c;  /* [M, 2] */
+  float* expec_f;         /* [M, 3] */
+  float* mkpts1_f;        /* [M, 2] */
+} LbFineMatchArgs;
+
+int lb_fine_match(const LbFineMatchArgs* args /*host*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOFTR_B200_H_ */

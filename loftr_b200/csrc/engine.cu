@@ -1,0 +1,717 @@
+// Host side of the C ABI (include/loftr_b200.h): tensor-map construction, kernel launches and the
+// per-stage orchestration of the matching hot path.  No torch types; raw device pointers + a stream.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/loftr_b200.h"
+#include "epilogues.cuh"
+#include "gemm_split.cuh"
+#include "simt_kernels.cuh"
+
+namespace lb {
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+#define LB_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define LB_TRY(expr)          \
+  do {                        \
+    int r__ = (expr);         \
+    if (r__ != 0) return r__; \
+  } while (0)
+
+#define LB_LAUNCHED()                 \
+  do {                                \
+    g_launches.fetch_add(1);          \
+    LB_CUDA(cudaGetLastError());      \
+  } while (0)
+
+static int device_check(int* sm_count) {
+  static std::once_flag once;
+  static int sms = 0, status = 0;
+  static char msg[256] = "";
+  std::call_once(once, [&]() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+      status = 1;
+      snprintf(msg, sizeof(msg), "no CUDA device: %s", cudaGetErrorString(e));
+      return;
+    }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) {
+      status = 1;
+      snprintf(msg, sizeof(msg), "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+      return;
+    }
+    if (prop.major != 10) {
+      status = 1;
+      snprintf(msg, sizeof(msg), "loftr_b200 requires an sm_100 (B200) device, found sm_%d%d; there is no fallback",
+               prop.major, prop.minor);
+      return;
+    }
+    sms = prop.multiProcessorCount;
+  });
+  if (status) return fail("%s", msg);
+  *sm_count = sms;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ TMA maps
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+  });
+  return fn;
+}
+
+// fp16 plane viewed as [batches][rows][K] with row stride ld and batch stride bs (elements);
+// box = 64 (K) x box_rows x 1, 128-byte swizzle, out-of-range elements read as zero.
+static int make_map(CUtensorMap* m, const void* base, long K, long rows, long batches, long ld, long bs,
+                    int box_rows) {
+  auto enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail("plane pointer not 16-byte aligned");
+  if ((ld * 2) % 16 != 0 || (bs * 2) % 16 != 0) return fail("plane strides must be multiples of 8 elements");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batches)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld * 2), static_cast<cuuint64_t>((bs > 0 ? bs : rows * ld) * 2)};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return 0;
+}
+
+struct Planes {
+  const void* hi;
+  const void* lo;
+  long ld;            // elements
+  long batch_stride;  // elements, 0 = not batched
+};
+
+// ------------------------------------------------------------------------------------------------ GEMM launch
+template <int BN, class Epi>
+static int launch_gemm(const Planes& A, const Planes& B, int batches, int M, int N, int K, int n_chunks,
+                       const typename Epi::Params& ep, cudaStream_t st) {
+  int sms = 0;
+  LB_TRY(device_check(&sms));
+  if (K % kBlockK != 0 || K <= 0) return fail("K=%d must be a positive multiple of %d", K, kBlockK);
+  if (M <= 0 || N <= 0 || batches <= 0) return 0;  // nothing to do
+  GemmShape s;
+  s.batches = batches;
+  s.M = M;
+  s.N = N;
+  s.K = K;
+  s.b_batched = B.batch_stride > 0 ? 1 : 0;
+  s.m_tiles = (M + kBlockM - 1) / kBlockM;
+  s.n_tiles = (N + BN - 1) / BN;
+  if (n_chunks <= 0 || n_chunks > s.n_tiles) n_chunks = s.n_tiles;
+  s.tiles_per_chunk = (s.n_tiles + n_chunks - 1) / n_chunks;
+  s.n_chunks = (s.n_tiles + s.tiles_per_chunk - 1) / s.tiles_per_chunk;
+
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  LB_TRY(make_map(&ma_hi, A.hi, K, M, batches, A.ld, A.batch_stride, kBlockM));
+  LB_TRY(make_map(&ma_lo, A.lo, K, M, batches, A.ld, A.batch_stride, kBlockM));
+  const int bb = s.b_batched ? batches : 1;
+  LB_TRY(make_map(&mb_hi, B.hi, K, N, bb, B.ld, B.batch_stride, BN));
+  LB_TRY(make_map(&mb_lo, B.lo, K, N, bb, B.ld, B.batch_stride, BN));
+
+  using S = GemmSmem<BN>;
+  constexpr int smem_bytes = S::kRingBytes + S::kBarBytes + Epi::kSmemBytes + 1024;
+  static_assert(smem_bytes <= 232448, "shared memory budget exceeded");
+  auto kern = gemm_split_kernel<BN, Epi>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = true;
+  }
+  const long items = static_cast<long>(batches) * s.m_tiles * s.n_chunks;
+  const int grid = static_cast<int>(items < sms ? items : sms);
+  kern<<<grid, kGemmThreads, smem_bytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, s, ep);
+  LB_LAUNCHED();
+  return 0;
+}
+
+// number of n-chunks that gives every SM a few work items when a CTA must sweep many n tiles
+static int pick_chunks(int row_items, int n_tiles, int sms) {
+  int c = 1;
+  while (static_cast<long>(row_items) * c < 4L * sms && c < n_tiles) ++c;
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------------ workspace
+struct Bump {
+  uint8_t* base;
+  size_t size;
+  size_t off = 0;
+  bool ok = true;
+  template <class T>
+  T* take(size_t count) {
+    const size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+    if (!base) {  // sizing pass
+      off += bytes;
+      return nullptr;
+    }
+    if (off + bytes > size) {
+      ok = false;
+      return nullptr;
+    }
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return p;
+  }
+};
+
+static inline int cdiv(long a, long b) { return static_cast<int>((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------ transformer
+struct TfWs {
+  float* qkv;       // [R, 3C]
+  __half* att_hi;   // [R, C]
+  __half* att_lo;
+  __half* h_hi;     // [R, 2C]
+  __half* h_lo;
+  float* kv;        // [2*n_groups, H, D*D + D]
+  float* kv_part;   // coarse only: [2*n_groups, H, splits, D*D + D]
+};
+constexpr int kKvSplits = 8;
+
+static void carve_tf(Bump& b, TfWs& w, int C, int H, long R, int n_groups, bool coarse) {
+  const int D = C / H;
+  w.qkv = b.take<float>(static_cast<size_t>(R) * 3 * C);
+  w.att_hi = b.take<__half>(static_cast<size_t>(R) * C);
+  w.att_lo = b.take<__half>(static_cast<size_t>(R) * C);
+  w.h_hi = b.take<__half>(static_cast<size_t>(R) * 2 * C);
+  w.h_lo = b.take<__half>(static_cast<size_t>(R) * 2 * C);
+  w.kv = b.take<float>(static_cast<size_t>(2) * n_groups * H * (D * D + D));
+  w.kv_part = coarse ? b.take<float>(static_cast<size_t>(2) * n_groups * H * kKvSplits * (D * D + D)) : nullptr;
+}
+
+template <int BN>
+static int tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, const LbTransformerState& st, const TfWs& w,
+                         long x_base, long x_rows, int x_group_rows, long s_base, long s_rows, int s_group_rows,
+                         int n_groups_x, bool self_pass, cudaStream_t stream);
+
+}  // namespace lb
+
+using namespace lb;
+
+// Runs one encoder-layer call `x <- layer(x, source)` for the row range x (queries) / s (source).
+// self_pass: x range == source range (q, k, v in one projection launch).
+template <int BN>
+static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, const LbTransformerState& st,
+                             const TfWs& w, long x_base, long x_rows, int x_group_rows, long s_base, long s_rows,
+                             int s_group_rows, int n_groups_x, bool self_pass, cudaStream_t stream) {
+  const int D = C / H;
+  const long ldc = 2L * C;
+  const __half* cat_hi = static_cast<const __half*>(st.cat_hi);
+  const __half* cat_lo = static_cast<const __half*>(st.cat_lo);
+  const uint8_t* mask = st.mask;
+
+  // 1. projections (+ elu+1 feature map + padding mask)      [transformer.py:47-49, linear_attention.py:31-39]
+  {
+    using Epi = EpiActStore<BN>;
+    if (self_pass) {
+      Planes A{cat_hi + x_base * ldc, cat_lo + x_base * ldc, ldc, 0};
+      Planes B{lw.wqkv_hi, lw.wqkv_lo, C, 0};
+      typename Epi::Params ep{w.qkv + x_base * 3 * C, 3 * C, 2 * C, mask ? mask + x_base : nullptr, nullptr, 0};
+      LB_TRY((launch_gemm<BN, Epi>(A, B, 1, static_cast<int>(x_rows), 3 * C, C, 0, ep, stream)));
+    } else {
+      Planes Aq{cat_hi + x_base * ldc, cat_lo + x_base * ldc, ldc, 0};
+      Planes Bq{lw.wqkv_hi, lw.wqkv_lo, C, 0};
+      typename Epi::Params eq{w.qkv + x_base * 3 * C, 3 * C, C, mask ? mask + x_base : nullptr, nullptr, 0};
+      LB_TRY((launch_gemm<BN, Epi>(Aq, Bq, 1, static_cast<int>(x_rows), C, C, 0, eq, stream)));
+      Planes Ak{cat_hi + s_base * ldc, cat_lo + s_base * ldc, ldc, 0};
+      Planes Bk{static_cast<const __half*>(lw.wqkv_hi) + static_cast<long>(C) * C,
+                static_cast<const __half*>(lw.wqkv_lo) + static_cast<long>(C) * C, C, 0};
+      typename Epi::Params ek{w.qkv + s_base * 3 * C + C, 3 * C, C, mask ? mask + s_base : nullptr, nullptr, 0};
+      LB_TRY((launch_gemm<BN, Epi>(Ak, Bk, 1, static_cast<int>(s_rows), 2 * C, C, 0, ek, stream)));
+    }
+  }
+  // 2. KV = K^T V and Ksum per (source group, head)            [linear_attention.py:43-44]
+  const int n_groups_s = static_cast<int>(s_rows / s_group_rows);
+  const int per = D * D + D;
+  if (D == 32) {
+    const int rps = cdiv(cdiv(s_group_rows, kKvSplits), 32) * 32;
+    const int splits = cdiv(s_group_rows, rps);
+    kv_partial_kernel<32><<<dim3(n_groups_s, H, splits), 256, 0, stream>>>(w.qkv, 3 * C, C, 2 * C, s_base,
+                                                                             s_group_rows, rps, w.kv_part);
+    LB_LAUNCHED();
+    const long total = static_cast<long>(n_groups_s) * H * per;
+    kv_merge_kernel<<<cdiv(total, 256), 256, 0, stream>>>(w.kv_part, splits, per, w.kv, total);
+    LB_LAUNCHED();
+  } else {
+    if (s_group_rows > 32) return fail("window transformer supports at most 32 rows per window");
+    kv_window_kernel<16, 8><<<n_groups_s, 256, 0, stream>>>(w.qkv, 3 * C, C, 2 * C, s_base, s_group_rows, w.kv);
+    LB_LAUNCHED();
+  }
+  // 3. message = (Q KV) / (Q Ksum + eps) -> planes             [linear_attention.py:45-46]
+  if (n_groups_x != n_groups_s && !self_pass) return fail("query / source group counts differ");
+  if (D == 32) {
+    const int rpb = 128;
+    attn_apply_kernel<32, 8><<<dim3(n_groups_x, cdiv(x_group_rows, rpb)), 256, 0, stream>>>(
+        w.qkv, 3 * C, 0, x_base, x_group_rows, rpb, w.kv, 1e-6f, w.att_hi, w.att_lo, C);
+  } else {
+    attn_apply_kernel<16, 8><<<dim3(n_groups_x, 1), 256, 0, stream>>>(w.qkv, 3 * C, 0, x_base, x_group_rows, 32,
+                                                                      w.kv, 1e-6f, w.att_hi, w.att_lo, C);
+  }
+  LB_LAUNCHED();
+  // 4. merge + norm1 -> cat[:, C:2C]                            [transformer.py:51-52]
+  {
+    using Epi = EpiLayerNorm<BN>;
+    Planes A{w.att_hi + x_base * C, w.att_lo + x_base * C, C, 0};
+    Planes B{lw.wm_hi, lw.wm_lo, C, 0};
+    typename Epi::Params ep{lw.ln1_g, lw.ln1_b, 1e-5f, nullptr, 0, nullptr, 0,
+                            static_cast<__half*>(st.cat_hi) + x_base * ldc,
+                            static_cast<__half*>(st.cat_lo) + x_base * ldc, static_cast<int>(ldc), C};
+    LB_TRY((launch_gemm<BN, Epi>(A, B, 1, static_cast<int>(x_rows), C, C, 0, ep, stream)));
+  }
+  // 5. mlp[0] + ReLU on cat([x, message]) -> h planes           [transformer.py:55, mlp 22-26]
+  {
+    using Epi = EpiPlanes<BN>;
+    Planes A{cat_hi + x_base * ldc, cat_lo + x_base * ldc, ldc, 0};
+    Planes B{lw.w1_hi, lw.w1_lo, 2 * C, 0};
+    typename Epi::Params ep{1, nullptr, 1, nullptr, 0, w.h_hi + x_base * ldc, w.h_lo + x_base * ldc,
+                            static_cast<int>(ldc), 0};
+    LB_TRY((launch_gemm<BN, Epi>(A, B, 1, static_cast<int>(x_rows), 2 * C, 2 * C, 0, ep, stream)));
+  }
+  // 6. mlp[2] + norm2 + residual -> x_f32 and cat[:, 0:C]        [transformer.py:55-58]
+  {
+    using Epi = EpiLayerNorm<BN>;
+    Planes A{w.h_hi + x_base * ldc, w.h_lo + x_base * ldc, ldc, 0};
+    Planes B{lw.w2_hi, lw.w2_lo, 2 * C, 0};
+    float* xf = st.x_f32 + x_base * C;
+    typename Epi::Params ep{lw.ln2_g, lw.ln2_b, 1e-5f, xf, C, xf, C,
+                            static_cast<__half*>(st.cat_hi) + x_base * ldc,
+                            static_cast<__half*>(st.cat_lo) + x_base * ldc, static_cast<int>(ldc), 0};
+    LB_TRY((launch_gemm<BN, Epi>(A, B, 1, static_cast<int>(x_rows), C, 2 * C, 0, ep, stream)));
+  }
+  return 0;
+}
+
+extern "C" {
+
+int lb_version(void) { return 100; }
+const char* lb_last_error(void) { return g_err; }
+long long lb_launch_count(void) { return g_launches.load(); }
+
+int lb_split_planes(const float* x, long rows, int cols, int ld_x, void* hi, void* lo, int ld_pl, int col0,
+                    void* stream) {
+  int sms;
+  LB_TRY(device_check(&sms));
+  if (rows <= 0 || cols <= 0) return 0;
+  const long total = rows * cols;
+  const int grid = static_cast<int>(total / 256 + 1 < 4096 ? total / 256 + 1 : 4096);
+  split_planes_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, rows, cols, ld_x, static_cast<__half*>(hi), static_cast<__half*>(lo), ld_pl, col0);
+  LB_LAUNCHED();
+  return 0;
+}
+
+int lb_gemm_split(const void* a_hi, const void* a_lo, long lda, long a_batch_stride, const void* b_hi,
+                  const void* b_lo, long ldb, long b_batch_stride, float* out, long ldo, long o_batch_stride,
+                  int batches, int M, int N, int K, void* stream) {
+  if (N % 32 != 0) return fail("lb_gemm_split: N must be a multiple of 32");
+  if (batches > 1 && o_batch_stride != static_cast<long>(M) * ldo)
+    return fail("lb_gemm_split: output batches must be densely stacked (o_batch_stride == M*ldo)");
+  Planes A{a_hi, a_lo, lda, batches > 1 ? a_batch_stride : 0};
+  Planes B{b_hi, b_lo, ldb, b_batch_stride};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (N % 256 == 0 || N > 128) {
+    using Epi = EpiActStore<256>;
+    Epi::Params ep{out, static_cast<int>(ldo), 0, nullptr, nullptr, 0};
+    return launch_gemm<256, Epi>(A, B, batches, M, N, K, 0, ep, st);
+  }
+  using Epi = EpiActStore<128>;
+  Epi::Params ep{out, static_cast<int>(ldo), 0, nullptr, nullptr, 0};
+  return launch_gemm<128, Epi>(A, B, batches, M, N, K, 0, ep, st);
+}
+
+int lb_coarse_prep(const float* feat_nchw, const float* pe, int n_img, int C, int h, int w, int pe_h, int pe_w,
+                   float* x_f32, void* cat_hi, void* cat_lo, void* stream) {
+  int sms;
+  LB_TRY(device_check(&sms));
+  if (h > pe_h || w > pe_w) return fail("feature map %dx%d exceeds the position-encoding table %dx%d", h, w, pe_h, pe_w);
+  if (n_img <= 0) return 0;
+  dim3 grid(cdiv(static_cast<long>(h) * w, 32), cdiv(C, 32), n_img);
+  coarse_prep_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      feat_nchw, pe, C, h, w, pe_h, pe_w, x_f32, static_cast<__half*>(cat_hi), static_cast<__half*>(cat_lo));
+  LB_LAUNCHED();
+  return 0;
+}
+
+size_t lb_transformer_workspace_bytes(int d_model, int nhead, int n_groups, int group_rows0, int group_rows1) {
+  Bump b{nullptr, 0};
+  TfWs w;
+  const long R = static_cast<long>(n_groups) * (group_rows0 + group_rows1);
+  carve_tf(b, w, d_model, nhead, R, n_groups, d_model / nhead == 32);
+  return b.off + 256;
+}
+
+int lb_transformer_forward(const LbEncoderLayerWeights* layers, const int* kinds, int n_layers, int d_model,
+                           int nhead, const LbTransformerState* st, void* ws, size_t ws_bytes, void* stream) {
+  int sms;
+  LB_TRY(device_check(&sms));
+  const int C = d_model, H = nhead;
+  const bool coarse = (C == 256 && H == 8);
+  const bool fine = (C == 128 && H == 8);
+  if (!coarse && !fine) return fail("unsupported transformer shape d_model=%d nhead=%d (built: 256/8 and 128/8)", C, H);
+  if (st->n_groups <= 0) return 0;
+  const long rows0 = static_cast<long>(st->n_groups) * st->group_rows0;
+  const long rows1 = static_cast<long>(st->n_groups) * st->group_rows1;
+  if (!ws) return fail("workspace pointer is null");
+  Bump b{static_cast<uint8_t*>(ws), ws_bytes};
+  TfWs w;
+  carve_tf(b, w, C, H, rows0 + rows1, st->n_groups, coarse);
+  if (!b.ok) return fail("transformer workspace too small: need %zu bytes", lb_transformer_workspace_bytes(C, H, st->n_groups, st->group_rows0, st->group_rows1));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool same_groups = st->group_rows0 == st->group_rows1;
+  for (int l = 0; l < n_layers; ++l) {
+    const LbEncoderLayerWeights& lw = layers[l];
+    auto pass = [&](long xb, long xr, int xg, long sb, long sr, int sg, int ng, bool self_pass) -> int {
+      return coarse ? tf_layer_pass<256>(lw, C, H, *st, w, xb, xr, xg, sb, sr, sg, ng, self_pass, s)
+                    : tf_layer_pass<128>(lw, C, H, *st, w, xb, xr, xg, sb, sr, sg, ng, self_pass, s);
+    };
+    if (kinds[l] == LB_LAYER_SELF) {
+      // feat0 = layer(feat0, feat0); feat1 = layer(feat1, feat1)  [transformer.py:93-94]; same weights,
+      // independent -> one pass over both sets when the group sizes agree.
+      if (same_groups) {
+        LB_TRY(pass(0, rows0 + rows1, st->group_rows0, 0, rows0 + rows1, st->group_rows0, 2 * st->n_groups, true));
+      } else {
+        LB_TRY(pass(0, rows0, st->group_rows0, 0, rows0, st->group_rows0, st->n_groups, true));
+        LB_TRY(pass(rows0, rows1, st->group_rows1, rows0, rows1, st->group_rows1, st->n_groups, true));
+      }
+    } else if (kinds[l] == LB_LAYER_CROSS) {
+      // feat0 = layer(feat0, feat1); feat1 = layer(feat1, feat0_new)  [transformer.py:96-97]
+      LB_TRY(pass(0, rows0, st->group_rows0, rows0, rows1, st->group_rows1, st->n_groups, false));
+      LB_TRY(pass(rows0, rows1, st->group_rows1, 0, rows0, st->group_rows0, st->n_groups, false));
+    } else {
+      return fail("unknown layer kind %d", kinds[l]);
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ coarse matching
+struct CmWs {
+  float2* row_part;  // [n_chunks][n*L]
+  float2* col_part;  // [m_tiles][n*S]
+  ArgPart* row_apart;
+  ArgPart* col_apart;
+  float *row_t, *col_t;          // additive terms used by the argmax pass (-LSE or potentials, masked)
+  float *row_u, *col_v;          // true potentials (sinkhorn)
+  float *row_key, *col_key;
+  int *row_arg, *col_arg;
+  float *bin_u, *bin_v;          // dustbin potentials [n]
+  uint8_t *row_dead, *col_dead;
+  uint8_t* flag;
+  float* conf;
+  int *ext0, *ext1;
+};
+constexpr int kMaxChunks = 8;
+
+static void carve_cm(Bump& b, CmWs& w, int n, int L, int S) {
+  const size_t nl = static_cast<size_t>(n) * L, ns = static_cast<size_t>(n) * S;
+  const int m_tiles = (L + kBlockM - 1) / kBlockM;
+  w.row_part = b.take<float2>(nl * kMaxChunks);
+  w.col_part = b.take<float2>(ns * m_tiles);
+  w.row_apart = b.take<ArgPart>(nl * kMaxChunks);
+  w.col_apart = b.take<ArgPart>(ns * m_tiles);
+  w.row_t = b.take<float>(nl);
+  w.col_t = b.take<float>(ns);
+  w.row_u = b.take<float>(nl);
+  w.col_v = b.take<float>(ns);
+  w.row_key = b.take<float>(nl);
+  w.col_key = b.take<float>(ns);
+  w.row_arg = b.take<int>(nl);
+  w.col_arg = b.take<int>(ns);
+  w.bin_u = b.take<float>(n);
+  w.bin_v = b.take<float>(n);
+  w.row_dead = b.take<uint8_t>(nl);
+  w.col_dead = b.take<uint8_t>(ns);
+  w.flag = b.take<uint8_t>(nl);
+  w.conf = b.take<float>(nl);
+  w.ext0 = b.take<int>(2 * static_cast<size_t>(n));
+  w.ext1 = b.take<int>(2 * static_cast<size_t>(n));
+}
+
+size_t lb_coarse_match_workspace_bytes(int n_pairs, int L, int S) {
+  Bump b{nullptr, 0};
+  CmWs w;
+  carve_cm(b, w, n_pairs, L, S);
+  return b.off + 256;
+}
+
+int lb_coarse_match(const LbCoarseMatchArgs* a, void* ws, size_t ws_bytes, void* stream) {
+  int sms;
+  LB_TRY(device_check(&sms));
+  const int n = a->n_pairs, L = a->L, S = a->S, C = a->C;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n <= 0) {
+    LB_CUDA(cudaMemsetAsync(a->count, 0, sizeof(int), st));
+    return 0;
+  }
+  if (L != a->h0c * a->w0c || S != a->h1c * a->w1c) return fail("L/S do not match the coarse grid sizes");
+  if (C % kBlockK != 0) return fail("C=%d must be a multiple of 64", C);
+  if ((a->mask0 == nullptr) != (a->mask1 == nullptr)) return fail("mask0 and mask1 must be given together");
+  if (!ws) return fail("workspace pointer is null");
+  Bump b{static_cast<uint8_t*>(ws), ws_bytes};
+  CmWs w;
+  carve_cm(b, w, n, L, S);
+  if (!b.ok) return fail("coarse-match workspace too small: need %zu bytes", lb_coarse_match_workspace_bytes(n, L, S));
+
+  constexpr int BN = 256;
+  const long nl = static_cast<long>(n) * L, ns = static_cast<long>(n) * S;
+  const int m_tiles = (L + kBlockM - 1) / kBlockM;
+  const int n_tiles = (S + BN - 1) / BN;
+  int chunks = pick_chunks(n * m_tiles, n_tiles, sms);
+  if (chunks > kMaxChunks) chunks = kMaxChunks;
+  // launch_gemm re-derives (tiles_per_chunk, n_chunks) from this request; mirror it to size the merges
+  const int tpc = (n_tiles + chunks - 1) / chunks;
+  const int n_chunks = (n_tiles + tpc - 1) / tpc;
+
+  Planes A{a->f0_hi, a->f0_lo, a->ld, static_cast<long>(L) * a->ld};
+  Planes B{a->f1_hi, a->f1_lo, a->ld, static_cast<long>(S) * a->ld};
+  const bool masked = a->mask0 != nullptr;
+  if (masked) {
+    mask_extent_kernel<<<n, 128, 0, st>>>(a->mask0, a->h0c, a->w0c, w.ext0);
+    LB_LAUNCHED();
+    mask_extent_kernel<<<n, 128, 0, st>>>(a->mask1, a->h1c, a->w1c, w.ext1);
+    LB_LAUNCHED();
+  }
+  const int TB = 256;
+  float conf_bias = 0.f;
+  float alpha = 1.f;
+  float scale = 1.f;
+  const float* rowterm_for_conf = nullptr;
+
+  if (a->match_type == LB_MATCH_DUAL_SOFTMAX) {
+    // sim = <f0/sqrt(C), f1/sqrt(C)> / T                                    [coarse_matching.py:106-110]
+    scale = 1.f / (static_cast<float>(C) * a->temperature);
+    alpha = 2.f;
+    const float* ct = nullptr;
+    const float* rt = nullptr;
+    if (masked) {  // padded rows / columns leave every normaliser      [coarse_matching.py:115-118]
+      mask_term_kernel<<<cdiv(ns, TB), TB, 0, st>>>(nullptr, a->mask1, nullptr, ns, w.col_t);
+      LB_LAUNCHED();
+      mask_term_kernel<<<cdiv(nl, TB), TB, 0, st>>>(nullptr, a->mask0, nullptr, nl, w.row_t);
+      LB_LAUNCHED();
+      ct = w.col_t;
+      rt = w.row_t;
+    }
+    using Epi = EpiScoreLse<BN, true, true>;
+    Epi::Params ep{scale, ct, rt, w.row_part, w.col_part};
+    LB_TRY((launch_gemm<BN, Epi>(A, B, n, L, S, C, chunks, ep, st)));
+    // row_t = -rowLSE, col_t = -colLSE (kNegBig on padded entries)              [coarse_matching.py:119]
+    lse_merge_kernel<<<cdiv(nl, TB), TB, 0, st>>>(w.row_part, n_chunks, nl, 0.f, nullptr, nullptr, L, a->mask0, w.row_t);
+    LB_LAUNCHED();
+    lse_merge_kernel<<<cdiv(ns, TB), TB, 0, st>>>(w.col_part, m_tiles, ns, 0.f, nullptr, nullptr, S, a->mask1, w.col_t);
+    LB_LAUNCHED();
+    rowterm_for_conf = w.row_t;
+  } else if (a->match_type == LB_MATCH_SINKHORN) {
+    // sim = <f0, f1> / C ; log-domain Sinkhorn with dustbins              [coarse_matching.py:121-131]
+    if (!a->bin_score) return fail("sinkhorn matching needs bin_score");
+    scale = 1.f / static_cast<float>(C);
+    alpha = 1.f;
+    const float norm = -logf(static_cast<float>(L + S));
+    const float log_mu_bin = logf(static_cast<float>(S)) + norm;  // dustbin row mass   [superglue.py:161]
+    const float log_nu_bin = logf(static_cast<float>(L)) + norm;  // dustbin column mass [superglue.py:162]
+    // v = 0 (kNegBig on padded columns for the masked variant), bin_v = 0
+    mask_term_kernel<<<cdiv(ns, TB), TB, 0, st>>>(nullptr, a->mask1, nullptr, ns, w.col_t);
+    LB_LAUNCHED();
+    fill_kernel<<<cdiv(ns, TB), TB, 0, st>>>(w.col_v, 0.f, ns);
+    LB_LAUNCHED();
+    fill_kernel<<<cdiv(n, TB), TB, 0, st>>>(w.bin_v, 0.f, n);
+    LB_LAUNCHED();
+    for (int it = 0; it < a->skh_iters; ++it) {
+      // u_i = log_mu_i - LSE_j(Z_ij + v_j), j over S real columns + the dustbin column   [superglue.py:146]
+      {
+        using Epi = EpiScoreLse<BN, true, false>;
+        Epi::Params ep{scale, w.col_t, nullptr, w.row_part, w.col_part};
+        LB_TRY((launch_gemm<BN, Epi>(A, B, n, L, S, C, chunks, ep, st)));
+        lse_merge_kernel<<<cdiv(nl, TB), TB, 0, st>>>(w.row_part, n_chunks, nl, norm, a->bin_score, w.bin_v, L,
+                                                      a->mask0, w.row_u);
+        LB_LAUNCHED();
+      }
+      // dustbin row: u_L = log_mu_L - LSE_j(bin + v_j, bin + bin_v)                         [superglue.py:146]
+      bin_lse_kernel<<<n, 256, 0, st>>>(w.col_v, S, a->bin_score, w.bin_v, log_mu_bin, w.bin_u);
+      LB_LAUNCHED();
+      mask_term_kernel<<<cdiv(nl, TB), TB, 0, st>>>(w.row_u, a->mask0, nullptr, nl, w.row_t);
+      LB_LAUNCHED();
+      // v_j = log_nu_j - LSE_i(Z_ij + u_i), i over L real rows + the dustbin row            [superglue.py:147]
+      {
+        using Epi = EpiScoreLse<BN, false, true>;
+        Epi::Params ep{scale, nullptr, w.row_t, w.row_part, w.col_part};
+        LB_TRY((launch_gemm<BN, Epi>(A, B, n, L, S, C, chunks, ep, st)));
+        lse_merge_kernel<<<cdiv(ns, TB), TB, 0, st>>>(w.col_part, m_tiles, ns, norm, a->bin_score, w.bin_u, S,
+                                                      a->mask1, w.col_v);
+        LB_LAUNCHED();
+      }
+      bin_lse_kernel<<<n, 256, 0, st>>>(w.row_u, L, a->bin_score, w.bin_u, log_nu_bin, w.bin_v);
+      LB_LAUNCHED();
+      mask_term_kernel<<<cdiv(ns, TB), TB, 0, st>>>(w.col_v, a->mask1, nullptr, ns, w.col_t);
+      LB_LAUNCHED();
+    }
+    // assignment = exp(Z + u + v - norm)                                      [superglue.py:148,168-169]
+    conf_bias = -norm;
+    rowterm_for_conf = w.row_u;
+  } else {
+    return fail("unknown match_type %d", a->match_type);
+  }
+
+  // arg-maxima of the confidence along both directions                       [coarse_matching.py:187-189]
+  const uint8_t* row_dead = nullptr;
+  const uint8_t* col_dead = nullptr;
+  const int passes = (a->match_type == LB_MATCH_SINKHORN && a->skh_prefilter) ? 2 : 1;
+  for (int pass = 0; pass < passes; ++pass) {
+    using Epi = EpiScoreArgmax<BN>;
+    Epi::Params ep{scale, alpha, w.col_t, w.row_t, w.row_apart, w.col_apart};
+    LB_TRY((launch_gemm<BN, Epi>(A, B, n, L, S, C, chunks, ep, st)));
+    argmax_merge_kernel<<<cdiv(nl, TB), TB, 0, st>>>(w.row_apart, n_chunks, nl, w.row_key, w.row_arg);
+    LB_LAUNCHED();
+    argmax_merge_kernel<<<cdiv(ns, TB), TB, 0, st>>>(w.col_apart, m_tiles, ns, w.col_key, w.col_arg);
+    LB_LAUNCHED();
+    if (passes == 2 && pass == 0) {
+      // prefilter: rows / columns whose best partner is the dustbin are zeroed  [coarse_matching.py:136-140]
+      ot_dead_kernel<<<cdiv(nl, TB), TB, 0, st>>>(w.row_key, a->bin_score, w.bin_v, L, nl, w.row_dead);
+      LB_LAUNCHED();
+      ot_dead_kernel<<<cdiv(ns, TB), TB, 0, st>>>(w.col_key, a->bin_score, w.bin_u, S, ns, w.col_dead);
+      LB_LAUNCHED();
+      mask_term_kernel<<<cdiv(nl, TB), TB, 0, st>>>(w.row_u, a->mask0, w.row_dead, nl, w.row_t);
+      LB_LAUNCHED();
+      mask_term_kernel<<<cdiv(ns, TB), TB, 0, st>>>(w.col_v, a->mask1, w.col_dead, ns, w.col_t);
+      LB_LAUNCHED();
+      row_dead = w.row_dead;
+      col_dead = w.col_dead;
+    }
+  }
+
+  SelectParams sp;
+  sp.n_pairs = n; sp.L = L; sp.S = S;
+  sp.h0c = a->h0c; sp.w0c = a->w0c; sp.h1c = a->h1c; sp.w1c = a->w1c;
+  sp.border = a->border_rm;
+  sp.thr = a->thr;
+  sp.conf_bias = conf_bias;
+  sp.row_key = w.row_key; sp.row_arg = w.row_arg; sp.col_arg = w.col_arg;
+  sp.rowterm = rowterm_for_conf;
+  sp.mask0 = a->mask0; sp.mask1 = a->mask1;
+  sp.ext0 = masked ? w.ext0 : nullptr; sp.ext1 = masked ? w.ext1 : nullptr;
+  sp.row_dead = row_dead; sp.col_dead = col_dead;
+  sp.flag = w.flag; sp.conf = w.conf;
+  match_flag_kernel<<<cdiv(nl, TB), TB, 0, st>>>(sp);
+  LB_LAUNCHED();
+
+  CompactParams cp;
+  cp.total = nl; cp.L = L; cp.S = S; cp.w0c = a->w0c; cp.w1c = a->w1c;
+  cp.scale = a->img_scale; cp.scale0 = a->scale0; cp.scale1 = a->scale1;
+  cp.flag = w.flag; cp.conf = w.conf; cp.row_arg = w.row_arg;
+  cp.capacity = a->capacity;
+  cp.b_ids = a->b_ids; cp.i_ids = a->i_ids; cp.j_ids = a->j_ids;
+  cp.mconf = a->mconf; cp.mkpts0 = a->mkpts0_c; cp.mkpts1 = a->mkpts1_c; cp.count = a->count;
+  match_compact_kernel<<<1, 1024, 0, st>>>(cp);
+  LB_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ fine level
+size_t lb_fine_preprocess_workspace_bytes(long M, int W, int Cf) {
+  Bump b{nullptr, 0};
+  const size_t rows = static_cast<size_t>(2) * M * W * W;
+  b.take<__half>(rows * Cf);
+  b.take<__half>(rows * Cf);
+  b.take<float>(static_cast<size_t>(2) * M * Cf);
+  return b.off + 256;
+}
+
+int lb_fine_preprocess(const LbFinePreprocessArgs* a, void* ws, size_t ws_bytes, void* stream) {
+  int sms;
+  LB_TRY(device_check(&sms));
+  if (a->M <= 0) return 0;
+  if (a->Cf != 128 || a->Cc > 256) return fail("fine preprocess built for Cf=128, Cc<=256 (got %d, %d)", a->Cf, a->Cc);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int WW = a->W * a->W;
+  const long rows = 2 * a->M * WW;
+  if (!ws) return fail("workspace pointer is null");
+  Bump b{static_cast<uint8_t*>(ws), ws_bytes};
+  __half* win_hi = b.take<__half>(static_cast<size_t>(rows) * a->Cf);
+  __half* win_lo = b.take<__half>(static_cast<size_t>(rows) * a->Cf);
+  float* gbias = b.take<float>(static_cast<size_t>(2) * a->M * a->Cf);
+  if (!b.ok) return fail("fine-preprocess workspace too small");
+
+  FineGatherParams g;
+  g.feat0 = a->feat_f0; g.feat1 = a->feat_f1;
+  g.sn0 = a->sn0; g.sc0 = a->sc0; g.sh0 = a->sh0; g.sw0 = a->sw0;
+  g.sn1 = a->sn1; g.sc1 = a->sc1; g.sh1 = a->sh1; g.sw1 = a->sw1;
+  g.Hf0 = a->Hf0; g.Wf0 = a->Wf0; g.Hf1 = a->Hf1; g.Wf1 = a->Wf1;
+  g.w0c = a->w0c; g.w1c = a->w1c; g.stride = a->stride; g.W = a->W; g.Cf = a->Cf; g.M = a->M;
+  g.b_ids = a->b_ids; g.i_ids = a->i_ids; g.j_ids = a->j_ids;
+  g.out_hi = win_hi; g.out_lo = win_lo; g.ld = a->Cf;
+  fine_gather_kernel<<<static_cast<unsigned>(2 * a->M), 256, 0, st>>>(g);
+  LB_LAUNCHED();
+
+  FineBiasParams fb;
+  fb.feat_c = a->feat_c;
+  fb.set1_row_base = static_cast<long>(a->n_pairs) * a->L;
+  fb.L = a->L; fb.S = a->S; fb.Cc = a->Cc; fb.Cf = a->Cf; fb.M = a->M;
+  fb.b_ids = a->b_ids; fb.i_ids = a->i_ids; fb.j_ids = a->j_ids;
+  fb.Wd = a->down_w; fb.bd = a->down_b; fb.Wm = a->merge_w; fb.bm = a->merge_b;
+  fb.gbias = gbias;
+  fine_bias_kernel<<<static_cast<unsigned>(2 * a->M), 128, 0, st>>>(fb);
+  LB_LAUNCHED();
+
+  // merge_feat over [window | coarse] = window @ Wm[:, :Cf]^T + per-window bias     [fine_preprocess.py:52-56]
+  using Epi = EpiPlanes<128>;
+  Planes A{win_hi, win_lo, a->Cf, 0};
+  Planes B{a->merge_w_hi, a->merge_w_lo, a->Cf, 0};
+  Epi::Params ep{0, gbias, WW, a->x_f32, a->Cf, static_cast<__half*>(a->cat_hi), static_cast<__half*>(a->cat_lo),
+                 2 * a->Cf, 0};
+  return launch_gemm<128, Epi>(A, B, 1, static_cast<int>(rows), a->Cf, a->Cf, 0, ep, st);
+}
+
+int lb_fine_match(const LbFineMatchArgs* a, void* stream) {
+  int sms;
+  LB_TRY(device_check(&sms));
+  if (a->M <= 0) return 0;
+  if (a->W * a->W > 32) return fail("fine window %dx%d exceeds one warp", a->W, a->W);
+  FineMatchParams p;
+  p.f0 = a->f0; p.f1 = a->f1; p.W = a->W; p.C = a->C; p.M = a->M;
+  p.scale = a->img_scale; p.scale1 = a->scale1; p.b_ids = a->b_ids;
+  p.mkpts1_c = a->mkpts1_c; p.expec_f = a->expec_f; p.mkpts1_f = a->mkpts1_f;
+  const int warps_per_block = 8;
+  fine_match_kernel<<<cdiv(a->M, warps_per_block), warps_per_block * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  LB_LAUNCHED();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,524 @@
+// Epilogue functors for gemm_split_kernel.  Each one is the fused tail of a reference op group
+// (SURVEY.md §2a G1-G7): the thread that owns accumulator row r (TMEM lane r) applies the
+// elementwise / row-wise work that the reference runs as separate eager kernels.
+#pragma once
+#include <cuda_fp16.h>
+#include "gemm_split.cuh"
+
+namespace lb {
+
+constexpr float kNegBig = -1.0e30f;  // finite stand-in for -inf (keeps exp(x - max) NaN-free)
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// exp(x) for x <= 0 (softmax numerators)
+__device__ __forceinline__ float exp_fast(float x) { return ex2_approx(x * kLog2e); }
+
+__device__ __forceinline__ int epi_tid() { return threadIdx.x - kEpiWarp0 * 32; }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// x = hi + lo with both halves fp16 (round-to-nearest); |x| must stay below 65504.
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+
+// Write 32 consecutive values of one row as fp16 hi/lo planes (64 bytes each, 16B-aligned).
+__device__ __forceinline__ void store_planes32(__half* hi_ptr, __half* lo_ptr, const float (&x)[32]) {
+  uint32_t h[16], l[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    __half h0, l0, h1, l1;
+    split_f16(x[2 * j], h0, l0);
+    split_f16(x[2 * j + 1], h1, l1);
+    h[j] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
+    l[j] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
+  }
+  uint4* hp = reinterpret_cast<uint4*>(hi_ptr);
+  uint4* lp = reinterpret_cast<uint4*>(lo_ptr);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    hp[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+    lp[j] = make_uint4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
+  }
+}
+
+__device__ __forceinline__ void store_f32x32(float* p, const float (&x)[32]) {
+  float4* q = reinterpret_cast<float4*>(p);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) q[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+}
+
+__device__ __forceinline__ void load_acc32(uint32_t tmem_acc, int col, float (&x)[32]) {
+  uint32_t v[32];
+  const uint32_t lane_base = static_cast<uint32_t>((epi_tid() >> 5) * 32) << 16;
+  tmem_ld32(tmem_acc + col + lane_base, v);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[row, col] = act(acc) * rowmask[row];  act = elu(x)+1 for col < elu_cols, identity otherwise.
+// Covers q/k/v projection + feature map + padding mask of LinearAttention
+// (reference linear_attention.py:31-39: Q = elu(q)+1, K = elu(k)+1, Q*=q_mask, K*=kv_mask, V*=kv_mask).
+template <int BLOCK_N>
+struct EpiActStore {
+  struct Params {
+    float* out;              // [batches*M, ld]
+    int ld;
+    int elu_cols;            // columns [0, elu_cols) get elu+1
+    const uint8_t* rowmask;  // optional [batches*M] (1 = valid)
+    const uint8_t* rowmask2; // optional second mask applied to columns >= mask2_from (cross: never used)
+    int mask2_from;
+  };
+  static constexpr int kSmemBytes = 0;
+  const Params& p;
+  const GemmShape& s;
+  __device__ EpiActStore(const Params& p_, uint8_t*, const GemmShape& s_) : p(p_), s(s_) {}
+  __device__ void item_begin(int, int, int) {}
+  __device__ void item_end(int, int, int) {}
+  __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
+    const int r = m0 + epi_tid();
+    const bool row_ok = r < s.M;
+    const long grow = static_cast<long>(batch) * s.M + r;
+    float mk = 1.f;
+    if (row_ok && p.rowmask) mk = p.rowmask[grow] ? 1.f : 0.f;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      const int col = n0 + c * 32;
+      if (col >= s.N) break;  // warp-uniform
+      float x[32];
+      load_acc32(tmem_acc, c * 32, x);
+      if (col < p.elu_cols) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = x[j] > 0.f ? x[j] + 1.f : expf(x[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] *= mk;
+      if (row_ok) store_f32x32(p.out + grow * p.ld + col, x);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// y = LayerNorm(acc) * gamma + beta (+ residual) over the full row (requires N == BLOCK_N).
+// Covers merge+norm1 and mlp[2]+norm2+residual of LoFTREncoderLayer (reference transformer.py:51-58).
+template <int BLOCK_N>
+struct EpiLayerNorm {
+  struct Params {
+    const float* gamma;
+    const float* beta;
+    float eps;
+    const float* residual;  // optional [rows, ld_res]
+    int ld_res;
+    float* out_f32;         // optional [rows, ld_f32]
+    int ld_f32;
+    __half* out_hi;         // optional planes [rows, ld_pl], written at column offset pl_col0
+    __half* out_lo;
+    int ld_pl;
+    int pl_col0;
+  };
+  static constexpr int kSmemBytes = 2 * BLOCK_N * 4;
+  const Params& p;
+  const GemmShape& s;
+  float* sg;
+  float* sb;
+  __device__ EpiLayerNorm(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_) {
+    sg = reinterpret_cast<float*>(smem);
+    sb = sg + BLOCK_N;
+    for (int i = epi_tid(); i < BLOCK_N; i += kEpiThreads) {
+      sg[i] = p.gamma[i];
+      sb[i] = p.beta[i];
+    }
+    epi_bar_sync();
+  }
+  __device__ void item_begin(int, int, int) {}
+  __device__ void item_end(int, int, int) {}
+  __device__ void tile(uint32_t tmem_acc, int batch, int m0, int) {
+    const int r = m0 + epi_tid();
+    const bool row_ok = r < s.M;
+    const long grow = static_cast<long>(batch) * s.M + r;
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      float x[32];
+      load_acc32(tmem_acc, c * 32, x);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sum += x[j];
+    }
+    const float mean = sum * (1.f / BLOCK_N);
+    float sq = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      float x[32];
+      load_acc32(tmem_acc, c * 32, x);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float d = x[j] - mean;
+        sq += d * d;
+      }
+    }
+    const float rstd = rsqrtf(sq * (1.f / BLOCK_N) + p.eps);
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      float x[32];
+      load_acc32(tmem_acc, c * 32, x);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = (x[j] - mean) * rstd * sg[c * 32 + j] + sb[c * 32 + j];
+      if (row_ok) {
+        if (p.residual) {
+          const float4* rp = reinterpret_cast<const float4*>(p.residual + grow * p.ld_res + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = rp[j];
+            x[4 * j] += t.x;
+            x[4 * j + 1] += t.y;
+            x[4 * j + 2] += t.z;
+            x[4 * j + 3] += t.w;
+          }
+        }
+        if (p.out_f32) store_f32x32(p.out_f32 + grow * p.ld_f32 + c * 32, x);
+        if (p.out_hi) {
+          const long off = grow * p.ld_pl + p.pl_col0 + c * 32;
+          store_planes32(p.out_hi + off, p.out_lo + off, x);
+        }
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// h = relu(acc) -> fp16 planes (mlp[0]+ReLU, reference transformer.py:22-26,55)
+// or, with group_bias: y = acc + gbias[row / group_rows, col] -> fp32 + planes
+// (merge_feat over [window | repeated coarse feature], reference fine_preprocess.py:51-56: the
+// repeated half of the concatenation contributes one bias vector per window).
+template <int BLOCK_N>
+struct EpiPlanes {
+  struct Params {
+    int relu;
+    const float* gbias;   // optional [groups, N]
+    int group_rows;
+    float* out_f32;       // optional
+    int ld_f32;
+    __half* out_hi;
+    __half* out_lo;
+    int ld_pl;
+    int pl_col0;
+  };
+  static constexpr int kSmemBytes = 0;
+  const Params& p;
+  const GemmShape& s;
+  __device__ EpiPlanes(const Params& p_, uint8_t*, const GemmShape& s_) : p(p_), s(s_) {}
+  __device__ void item_begin(int, int, int) {}
+  __device__ void item_end(int, int, int) {}
+  __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
+    const int r = m0 + epi_tid();
+    const bool row_ok = r < s.M;
+    const long grow = static_cast<long>(batch) * s.M + r;
+    const float* gb = nullptr;
+    if (p.gbias && row_ok) gb = p.gbias + (grow / p.group_rows) * s.N;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      const int col = n0 + c * 32;
+      if (col >= s.N) break;
+      float x[32];
+      load_acc32(tmem_acc, c * 32, x);
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+      }
+      if (gb) {
+        const float4* bp = reinterpret_cast<const float4*>(gb + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = bp[j];
+          x[4 * j] += t.x;
+          x[4 * j + 1] += t.y;
+          x[4 * j + 2] += t.z;
+          x[4 * j + 3] += t.w;
+        }
+      }
+      if (row_ok) {
+        if (p.out_f32) store_f32x32(p.out_f32 + grow * p.ld_f32 + col, x);
+        if (p.out_hi) {
+          const long off = grow * p.ld_pl + p.pl_col0 + col;
+          store_planes32(p.out_hi + off, p.out_lo + off, x);
+        }
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Warp "transpose-reduce": every lane holds v[0..31] (its row's values for 32 columns); afterwards
+// lane j holds op over the warp's 32 rows of column j in v[0].  31 shuffles instead of 32*5.
+template <class T, class Op>
+__device__ __forceinline__ T warp_transpose_reduce(T (&v)[32], Op op) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int step = 16; step >= 1; step >>= 1) {
+    const bool up = (lane & step) != 0;
+#pragma unroll
+    for (int k = 0; k < step; ++k) {
+      const T send = up ? v[k] : v[k + step];
+      const T keep = up ? v[k + step] : v[k];
+      const T recv = __shfl_xor_sync(0xffffffffu, send, step);
+      v[k] = op(keep, recv);
+    }
+  }
+  return v[0];
+}
+
+struct OpMaxF { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+struct OpAddF { __device__ float operator()(float a, float b) const { return a + b; } };
+struct OpMaxU64 {
+  __device__ unsigned long long operator()(unsigned long long a, unsigned long long b) const {
+    return a > b ? a : b;
+  }
+};
+
+// order-preserving map float -> uint32
+__device__ __forceinline__ uint32_t f32_ordered(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_unordered(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pass 1 of the fused coarse matching: z = acc * scale is one 128 x BLOCK_N tile of the similarity
+// matrix (reference coarse_matching.py:109-110 / 122).  Emits log-sum-exp partials
+//   rows:    (max, sum) over this work item's columns of  z[i,j] + colterm[j]
+//   columns: (max, sum) over this tile's 128 rows of      z[i,j] + rowterm[i]
+// without ever storing z.  With colterm = rowterm = 0 these are the two softmax normalisers of the
+// dual-softmax (coarse_matching.py:119); with the Sinkhorn potentials they are one half-iteration of
+// log_sinkhorn_iterations (third_party superglue.py:141-148).  Masked / out-of-range entries carry
+// the term kNegBig and therefore vanish from every sum (coarse_matching.py:115-118 fills -1e9).
+template <int BLOCK_N, bool kRows, bool kCols>
+struct EpiScoreLse {
+  struct Params {
+    float scale;
+    const float* colterm;   // optional [batches*N]; nullptr -> 0
+    const float* rowterm;   // optional [batches*M]
+    float2* row_part;       // [n_chunks][batches*M]
+    float2* col_part;       // [m_tiles][batches*N]
+  };
+  // colterm staging + per-warp column partials + per-warp column-max broadcast
+  static constexpr int kSmemBytes = BLOCK_N * 4 + 4 * BLOCK_N * 8 + 4 * 32 * 4;
+  const Params& p;
+  const GemmShape& s;
+  float* s_ct;       // [BLOCK_N]
+  float2* s_cpart;   // [4][BLOCK_N]
+  float* s_cmax;     // [4][32]
+  float row_m, row_l;
+
+  __device__ EpiScoreLse(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_) {
+    s_ct = reinterpret_cast<float*>(smem);
+    s_cpart = reinterpret_cast<float2*>(smem + BLOCK_N * 4);
+    s_cmax = reinterpret_cast<float*>(smem + BLOCK_N * 4 + 4 * BLOCK_N * 8);
+  }
+  __device__ void item_begin(int, int, int) {
+    row_m = kNegBig;
+    row_l = 0.f;
+  }
+  __device__ void item_end(int batch, int m0, int chunk) {
+    if (kRows) {
+      const int r = m0 + epi_tid();
+      if (r < s.M) {
+        p.row_part[static_cast<long>(chunk) * s.batches * s.M + static_cast<long>(batch) * s.M + r] =
+            make_float2(row_m, row_l);
+      }
+    }
+  }
+  __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
+    const int t = epi_tid();
+    const int w = t >> 5;
+    const int lane = t & 31;
+    const int r = m0 + t;
+    // stage column terms of this tile
+    for (int j = t; j < BLOCK_N; j += kEpiThreads) {
+      const int col = n0 + j;
+      float ct = kNegBig;
+      if (col < s.N) ct = p.colterm ? p.colterm[static_cast<long>(batch) * s.N + col] : 0.f;
+      s_ct[j] = ct;
+    }
+    float rt = kNegBig;
+    if (r < s.M) rt = p.rowterm ? p.rowterm[static_cast<long>(batch) * s.M + r] : 0.f;
+    epi_bar_sync();
+
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      if (n0 + c * 32 >= s.N) break;
+      float z[32];
+      load_acc32(tmem_acc, c * 32, z);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) z[j] *= p.scale;
+
+      if (kRows) {
+        float x[32];
+        float cm = kNegBig;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          x[j] = z[j] + s_ct[c * 32 + j];
+          cm = fmaxf(cm, x[j]);
+        }
+        const float m_new = fmaxf(row_m, cm);
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc += exp_fast(x[j] - m_new);
+        row_l = row_l * exp_fast(row_m - m_new) + acc;
+        row_m = m_new;
+      }
+      if (kCols) {
+        float y[32], v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          y[j] = z[j] + rt;
+          v[j] = y[j];
+        }
+        const float cmax = warp_transpose_reduce(v, OpMaxF());  // lane j: max of column c*32+j
+        s_cmax[w * 32 + lane] = cmax;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = exp_fast(y[j] - s_cmax[w * 32 + j]);
+        __syncwarp();
+        const float csum = warp_transpose_reduce(v, OpAddF());
+        s_cpart[w * BLOCK_N + c * 32 + lane] = make_float2(cmax, csum);
+      }
+    }
+    if (kCols) {
+      epi_bar_sync();
+      // merge the four 32-row partials of each column and emit the 128-row partial
+      for (int j = t; j < BLOCK_N; j += kEpiThreads) {
+        const int col = n0 + j;
+        if (col < s.N) {
+          float m = kNegBig;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) m = fmaxf(m, s_cpart[q * BLOCK_N + j].x);
+          float l = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 pq = s_cpart[q * BLOCK_N + j];
+            l += pq.y * exp_fast(pq.x - m);
+          }
+          p.col_part[static_cast<long>(m0 / kBlockM) * s.batches * s.N + static_cast<long>(batch) * s.N + col] =
+              make_float2(m, l);
+        }
+      }
+    }
+    epi_bar_sync();  // s_ct / s_cpart are reused by the next tile
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Pass 2: recompute the tile and take arg-maxima of the confidence along both directions.
+//   row key  = alpha*z[i,j] + colterm[j]   (arg max over j: nearest neighbour of row i)
+//   col key  = alpha*z[i,j] + rowterm[i]   (arg max over i: nearest neighbour of column j)
+// dual-softmax: alpha=2, colterm=-colLSE, rowterm=-rowLSE (log conf = 2z - rowLSE_i - colLSE_j,
+// monotone in the key along each direction); Sinkhorn: alpha=1, terms = potentials v, u.
+// Replaces conf.max(dim=2) / conf.max(dim=1) of the mutual-nearest test (coarse_matching.py:187-189).
+struct ArgPart {
+  float key;
+  int idx;
+};
+template <int BLOCK_N>
+struct EpiScoreArgmax {
+  struct Params {
+    float scale;
+    float alpha;
+    const float* colterm;  // [batches*N] (kNegBig disables a column)
+    const float* rowterm;  // [batches*M]
+    ArgPart* row_part;     // [n_chunks][batches*M]
+    ArgPart* col_part;     // [m_tiles][batches*N]
+  };
+  static constexpr int kSmemBytes = BLOCK_N * 4 + 4 * BLOCK_N * 8;
+  const Params& p;
+  const GemmShape& s;
+  float* s_ct;
+  unsigned long long* s_cpart;  // [4][BLOCK_N]
+  float best_key;
+  int best_j;
+
+  __device__ EpiScoreArgmax(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_) {
+    s_ct = reinterpret_cast<float*>(smem);
+    s_cpart = reinterpret_cast<unsigned long long*>(smem + BLOCK_N * 4);
+  }
+  __device__ void item_begin(int, int, int) {
+    best_key = -3.0e38f;
+    best_j = -1;
+  }
+  __device__ void item_end(int batch, int m0, int chunk) {
+    const int r = m0 + epi_tid();
+    if (r < s.M) {
+      ArgPart a;
+      a.key = best_key;
+      a.idx = best_j;
+      p.row_part[static_cast<long>(chunk) * s.batches * s.M + static_cast<long>(batch) * s.M + r] = a;
+    }
+  }
+  __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
+    const int t = epi_tid();
+    const int w = t >> 5;
+    const int lane = t & 31;
+    const int r = m0 + t;
+    for (int j = t; j < BLOCK_N; j += kEpiThreads) {
+      const int col = n0 + j;
+      s_ct[j] = (col < s.N) ? p.colterm[static_cast<long>(batch) * s.N + col] : kNegBig;
+    }
+    const float rt = (r < s.M) ? p.rowterm[static_cast<long>(batch) * s.M + r] : kNegBig;
+    const float sa = p.scale * p.alpha;
+    epi_bar_sync();
+
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      if (n0 + c * 32 >= s.N) break;
+      float z[32];
+      load_acc32(tmem_acc, c * 32, z);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) z[j] *= sa;
+      // row direction: thread-local, strict '>' keeps the first (smallest j) maximum
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float key = z[j] + s_ct[c * 32 + j];
+        if (key > best_key) {
+          best_key = key;
+          best_j = n0 + c * 32 + j;
+        }
+      }
+      // column direction: arg max over the warp's 32 rows; ties -> smallest row
+      unsigned long long v[32];
+      const unsigned long long tag = 0xFFFFFFFFull - static_cast<unsigned long long>(static_cast<uint32_t>(r));
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = (static_cast<unsigned long long>(f32_ordered(z[j] + rt)) << 32) | tag;
+      }
+      const unsigned long long best = warp_transpose_reduce(v, OpMaxU64());
+      s_cpart[w * BLOCK_N + c * 32 + lane] = best;
+    }
+    epi_bar_sync();
+    for (int j = t; j < BLOCK_N; j += kEpiThreads) {
+      const int col = n0 + j;
+      if (col < s.N) {
+        unsigned long long b = s_cpart[j];
+#pragma unroll
+        for (int q = 1; q < 4; ++q) {
+          const unsigned long long o = s_cpart[q * BLOCK_N + j];
+          b = o > b ? o : b;
+        }
+        ArgPart a;
+        a.key = f32_unordered(static_cast<uint32_t>(b >> 32));
+        a.idx = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(b & 0xFFFFFFFFull));
+        p.col_part[static_cast<long>(m0 / kBlockM) * s.batches * s.N + static_cast<long>(batch) * s.N + col] = a;
+      }
+    }
+    epi_bar_sync();
+  }
+};
+
+}  // namespace lb

@@ -1,0 +1,222 @@
+// Split-precision tensor-core contraction core shared by every dense product on the hot path.
+//
+//   D[b, m, n] = sum_k A[b, m, k] * B[b?, n, k]          (A and B both K-major, "NT" form)
+//
+// which is exactly the form of nn.Linear (x @ W^T; reference src/loftr/loftr_module/transformer.py:47-49,
+// 51,55) and of the coarse score matrix einsum('nlc,nsc->nls') (src/loftr/utils/coarse_matching.py:109).
+//
+// Precision: the reference computes these products in fp32.  The mconf tolerance (rtol 1e-3 on logits
+// of magnitude ~100) rules out single-pass fp16/bf16/tf32 operands (SURVEY.md §7 hard part 1), so each
+// operand lives in HBM as two fp16 planes, x = hi + lo (|lo| <= ulp(hi)/2), and every k-step issues
+// three tcgen05.mma (hi*hi + hi*lo + lo*hi) into one fp32 TMEM accumulator.  The dropped lo*lo term is
+// <= 2^-22 relative.
+//
+// Structure (one persistent CTA per SM, 256 threads):
+//   warp 0   : TMA producer    (global -> 128B-swizzled smem ring, 4 tiles per stage)
+//   warp 1   : MMA issuer      (one elected lane, tcgen05.mma cta_group::1, M=128, N=BLOCK_N, K=16)
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue        (tcgen05.ld: thread t owns accumulator row t of the 128-row tile)
+// The fp32 accumulator is double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include "ptx.cuh"
+
+namespace lb {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 fp16 = 128 bytes = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 256;
+constexpr int kEpiThreads = 128;
+constexpr int kEpiWarp0 = 4;
+
+struct GemmShape {
+  int batches;      // independent problems along the tensor maps' 3rd dimension
+  int M;            // rows of A per batch
+  int N;            // rows of B per batch (= output columns)
+  int K;            // multiple of 64
+  int b_batched;    // 1: B has its own batch slice (score matrix); 0: B shared (weights)
+  int m_tiles;      // ceil(M / 128)
+  int n_tiles;      // ceil(N / BLOCK_N)
+  int n_chunks;     // a work item = (batch, m_tile, chunk); chunk = tiles_per_chunk consecutive n tiles
+  int tiles_per_chunk;
+};
+
+template <int BLOCK_N>
+struct GemmSmem {
+  static constexpr int kATile = kBlockM * kBlockK * 2;      // 16 KB
+  static constexpr int kBTile = BLOCK_N * kBlockK * 2;      // 16/32 KB
+  static constexpr int kStageBytes = 2 * kATile + 2 * kBTile;
+  static constexpr int kStages = (BLOCK_N == 256) ? 2 : 3;
+  static constexpr int kRingBytes = kStages * kStageBytes;  // 192 KB
+  static constexpr int kBarBytes = 256;
+};
+
+// Epilogue contract (all methods are called by the 128 epilogue threads only):
+//   struct Params;                               // trivially copyable, passed by value to the kernel
+//   static constexpr int kSmemBytes;             // extra dynamic smem the epilogue wants
+//   __device__ Epi(const Params&, uint8_t* smem, const GemmShape&);
+//   __device__ void item_begin(int batch, int m0, int chunk);
+//   __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0);   // tmem_acc: column base of this
+//                                                                         // tile's accumulator (lane field 0)
+//   __device__ void item_end(int batch, int m0, int chunk);
+template <int BLOCK_N, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                  const GemmShape shape, const typename Epi::Params epi_params) {
+  using S = GemmSmem<BLOCK_N>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // Dynamic smem base is only guaranteed 16B aligned; the swizzled tiles need 1024B.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kRingBytes);
+  uint64_t* empty_bar = full_bar + S::kStages;
+  uint64_t* tmem_full = empty_bar + S::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* epi_smem = smem + S::kRingBytes + S::kBarBytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // 256 or 512: power of two
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a_hi);
+    tma_prefetch_desc(&tm_a_lo);
+    tma_prefetch_desc(&tm_b_hi);
+    tma_prefetch_desc(&tm_b_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], kEpiThreads);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_kb = shape.K / kBlockK;
+  const int total_items = shape.batches * shape.m_tiles * shape.n_chunks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int chunk = item % shape.n_chunks;
+        const int mt = (item / shape.n_chunks) % shape.m_tiles;
+        const int batch = item / (shape.n_chunks * shape.m_tiles);
+        const int nt_begin = chunk * shape.tiles_per_chunk;
+        const int nt_end = min(nt_begin + shape.tiles_per_chunk, shape.n_tiles);
+        for (int nt = nt_begin; nt < nt_end; ++nt) {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = ring + stage * S::kStageBytes;
+            mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+            tma_load_3d(st, &tm_a_hi, &full_bar[stage], kb * kBlockK, mt * kBlockM, batch);
+            tma_load_3d(st + S::kATile, &tm_a_lo, &full_bar[stage], kb * kBlockK, mt * kBlockM, batch);
+            const int bb = shape.b_batched ? batch : 0;
+            tma_load_3d(st + 2 * S::kATile, &tm_b_hi, &full_bar[stage], kb * kBlockK, nt * BLOCK_N, bb);
+            tma_load_3d(st + 2 * S::kATile + S::kBTile, &tm_b_lo, &full_bar[stage], kb * kBlockK,
+                        nt * BLOCK_N, bb);
+            if (++stage == S::kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16_f32(kBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int chunk = item % shape.n_chunks;
+        const int nt_begin = chunk * shape.tiles_per_chunk;
+        const int nt_end = min(nt_begin + shape.tiles_per_chunk, shape.n_tiles);
+        for (int nt = nt_begin; nt < nt_end; ++nt) {
+          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t st = smem_u32(ring + stage * S::kStageBytes);
+            const uint64_t da_hi = umma_desc_k_sw128(st);
+            const uint64_t da_lo = umma_desc_k_sw128(st + S::kATile);
+            const uint64_t db_hi = umma_desc_k_sw128(st + 2 * S::kATile);
+            const uint64_t db_lo = umma_desc_k_sw128(st + 2 * S::kATile + S::kBTile);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              // advance 16 fp16 = 32 bytes along K inside the 128B swizzle row: +2 in 16-byte units
+              const uint64_t adv = static_cast<uint64_t>(k * 2);
+              umma_f16(d_tmem, da_hi + adv, db_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
+              umma_f16(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == S::kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          umma_commit(&tmem_full[acc]);
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------------------------------------ epilogue
+    Epi epi(epi_params, epi_smem, shape);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int chunk = item % shape.n_chunks;
+      const int mt = (item / shape.n_chunks) % shape.m_tiles;
+      const int batch = item / (shape.n_chunks * shape.m_tiles);
+      const int nt_begin = chunk * shape.tiles_per_chunk;
+      const int nt_end = min(nt_begin + shape.tiles_per_chunk, shape.n_tiles);
+      epi.item_begin(batch, mt * kBlockM, chunk);
+      for (int nt = nt_begin; nt < nt_end; ++nt) {
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        epi.tile(tmem_base + acc * BLOCK_N, batch, mt * kBlockM, nt * BLOCK_N);
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+      epi.item_end(batch, mt * kBlockM, chunk);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace lb
