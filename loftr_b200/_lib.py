@@ -1,0 +1,130 @@
+"""ctypes binding of the C ABI declared in include/loftr_b200.h.
+
+The CUDA library is mandatory: there is no PyTorch / CPU fallback for the hot path.  Importing this
+module on a machine where the library has not been built raises immediately; calling a compute entry
+point without an sm_100 device fails inside the library with a clear message.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libloftr_b200.so")
+
+MATCH_DUAL_SOFTMAX = 0
+MATCH_SINKHORN = 1
+LAYER_SELF = 0
+LAYER_CROSS = 1
+
+c_void_p = C.c_void_p
+c_int = C.c_int
+c_long = C.c_long
+c_float = C.c_float
+c_size_t = C.c_size_t
+
+
+class LbEncoderLayerWeights(C.Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "wqkv_hi", "wqkv_lo", "wm_hi", "wm_lo", "w1_hi", "w1_lo", "w2_hi", "w2_lo",
+        "ln1_g", "ln1_b", "ln2_g", "ln2_b")]
+
+
+class LbTransformerState(C.Structure):
+    _fields_ = [("x_f32", c_void_p), ("cat_hi", c_void_p), ("cat_lo", c_void_p), ("mask", c_void_p),
+                ("n_groups", c_int), ("group_rows0", c_int), ("group_rows1", c_int)]
+
+
+class LbCoarseMatchArgs(C.Structure):
+    _fields_ = [
+        ("f0_hi", c_void_p), ("f0_lo", c_void_p), ("f1_hi", c_void_p), ("f1_lo", c_void_p),
+        ("ld", c_int), ("n_pairs", c_int), ("L", c_int), ("S", c_int), ("C", c_int),
+        ("h0c", c_int), ("w0c", c_int), ("h1c", c_int), ("w1c", c_int),
+        ("match_type", c_int), ("temperature", c_float), ("thr", c_float), ("border_rm", c_int),
+        ("bin_score", c_void_p), ("skh_iters", c_int), ("skh_prefilter", c_int),
+        ("mask0", c_void_p), ("mask1", c_void_p),
+        ("img_scale", c_float), ("scale0", c_void_p), ("scale1", c_void_p),
+        ("capacity", c_long),
+        ("b_ids", c_void_p), ("i_ids", c_void_p), ("j_ids", c_void_p),
+        ("mconf", c_void_p), ("mkpts0_c", c_void_p), ("mkpts1_c", c_void_p), ("count", c_void_p),
+    ]
+
+
+class LbFinePreprocessArgs(C.Structure):
+    _fields_ = [
+        ("feat_f0", c_void_p), ("feat_f1", c_void_p),
+        ("sn0", c_long), ("sc0", c_long), ("sh0", c_long), ("sw0", c_long),
+        ("sn1", c_long), ("sc1", c_long), ("sh1", c_long), ("sw1", c_long),
+        ("Hf0", c_int), ("Wf0", c_int), ("Hf1", c_int), ("Wf1", c_int),
+        ("w0c", c_int), ("w1c", c_int), ("stride", c_int), ("W", c_int), ("Cf", c_int), ("Cc", c_int),
+        ("feat_c", c_void_p), ("n_pairs", c_int), ("L", c_int), ("S", c_int), ("M", c_long),
+        ("b_ids", c_void_p), ("i_ids", c_void_p), ("j_ids", c_void_p),
+        ("down_w", c_void_p), ("down_b", c_void_p), ("merge_w", c_void_p), ("merge_b", c_void_p),
+        ("merge_w_hi", c_void_p), ("merge_w_lo", c_void_p),
+        ("x_f32", c_void_p), ("cat_hi", c_void_p), ("cat_lo", c_void_p),
+    ]
+
+
+class LbFineMatchArgs(C.Structure):
+    _fields_ = [
+        ("f0", c_void_p), ("f1", c_void_p), ("W", c_int), ("C", c_int), ("M", c_long),
+        ("img_scale", c_float), ("scale1", c_void_p), ("b_ids", c_void_p), ("mkpts1_c", c_void_p),
+        ("expec_f", c_void_p), ("mkpts1_f", c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); the same list is what tests/test_abi.py checks against the header.
+SIGNATURES = {
+    "lb_version": (c_int, []),
+    "lb_last_error": (C.c_char_p, []),
+    "lb_launch_count": (C.c_longlong, []),
+    "lb_split_planes": (c_int, [c_void_p, c_long, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "lb_gemm_split": (c_int, [c_void_p, c_void_p, c_long, c_long, c_void_p, c_void_p, c_long, c_long, c_void_p,
+                              c_long, c_long, c_int, c_int, c_int, c_int, c_void_p]),
+    "lb_coarse_prep": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                               c_void_p, c_void_p]),
+    "lb_transformer_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "lb_transformer_forward": (c_int, [C.POINTER(LbEncoderLayerWeights), C.POINTER(c_int), c_int, c_int, c_int,
+                                       C.POINTER(LbTransformerState), c_void_p, c_size_t, c_void_p]),
+    "lb_coarse_match_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "lb_coarse_match": (c_int, [C.POINTER(LbCoarseMatchArgs), c_void_p, c_size_t, c_void_p]),
+    "lb_fine_preprocess_workspace_bytes": (c_size_t, [c_long, c_int, c_int]),
+    "lb_fine_preprocess": (c_int, [C.POINTER(LbFinePreprocessArgs), c_void_p, c_size_t, c_void_p]),
+    "lb_fine_match": (c_int, [C.POINTER(LbFineMatchArgs), c_void_p]),
+}
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libloftr_b200.so (once).  Raises LibraryMissing when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(
+            f"{LIB_PATH} not found: build it with `make` (or `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "loftr_b200 has no CPU or PyTorch fallback for the matching hot path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load().lb_last_error()
+        raise RuntimeError("loftr_b200: " + (msg.decode() if msg else f"error code {rc}"))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else t.data_ptr()

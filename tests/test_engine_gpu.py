@@ -1,0 +1,216 @@
+"""Parity tests proper: the CUDA engine (through the C ABI) against the numpy oracle and against the
+golden vectors of the reference.  Tolerances are BASELINE.json's: |dxy| < 0.5 px on keypoints, mconf
+rtol 1e-3 (match sets compared by key with near-tie adjudication)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import util
+from cases import CASES, CM_CASES, build_cfg, build_cm_inputs, build_inputs
+from oracle import loftr_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _t(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+# ------------------------------------------------------------------------------------------------ contraction core
+@pytest.mark.parametrize("shape", [(1, 128, 256, 64), (1, 300, 768, 256), (1, 1000, 128, 128), (2, 200, 512, 256),
+                                   (1, 1200, 384, 128), (1, 77, 256, 512)])
+def test_gemm_split_matches_fp64(shape):
+    from loftr_b200 import _lib
+    from loftr_b200.loftr import split_planes, _stream
+    b, m, n, k = shape
+    rs = np.random.RandomState(0)
+    a = (rs.standard_normal((b * m, k)) * 3 + 1).astype(np.float32)
+    w = (rs.standard_normal((b * n, k)) * 3 + 1).astype(np.float32)
+    ta, tw = _t(a), _t(w)
+    ah, al = split_planes(ta)
+    wh, wl = split_planes(tw)
+    out = torch.empty(b * m, n, dtype=torch.float32, device=DEV)
+    lib = _lib.load()
+    _lib.check(lib.lb_gemm_split(ah.data_ptr(), al.data_ptr(), k, m * k, wh.data_ptr(), wl.data_ptr(), k,
+                                 n * k if b > 1 else 0, out.data_ptr(), n, m * n, b, m, n, k, _stream()))
+    ref = np.einsum("bmk,bnk->bmn", a.reshape(b, m, k).astype(np.float64), w.reshape(b, n, k).astype(np.float64))
+    got = out.cpu().numpy().reshape(b, m, n)
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 5e-6
+
+
+# ------------------------------------------------------------------------------------------------ transformer
+def _layer_weights(model_tf):
+    names = ["q_proj.weight", "k_proj.weight", "v_proj.weight", "merge.weight", "mlp.0.weight", "mlp.2.weight",
+             "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias"]
+    sd = {k: v.detach().cpu().numpy() for k, v in model_tf.state_dict().items()}
+    return [{k: sd[f"layers.{i}.{k}"] for k in names} for i in range(len(model_tf.layers))]
+
+
+@pytest.mark.parametrize("cfgname", ["coarse_equal", "coarse_masked_unequal", "fine_windows"])
+def test_transformer_matches_oracle(cfgname):
+    case = CASES[0]
+    model, cfg, _ = util.build_model(case, DEV)
+    rs = np.random.RandomState(3)
+    if cfgname == "fine_windows":
+        tf, tcfg = model.loftr_fine, cfg["fine"]
+        n, l, s, c = 37, 25, 25, 128
+        m0 = m1 = None
+    else:
+        tf, tcfg = model.loftr_coarse, cfg["coarse"]
+        c = 256
+        if cfgname == "coarse_equal":
+            n, l, s = 2, 300, 300
+            m0 = m1 = None
+        else:
+            n, l, s = 2, 280, 200
+            m0 = rs.uniform(size=(n, l)) > 0.2
+            m1 = rs.uniform(size=(n, s)) > 0.3
+    f0 = rs.standard_normal((n, l, c)).astype(np.float32)
+    f1 = rs.standard_normal((n, s, c)).astype(np.float32)
+    o0, o1 = O.local_feature_transformer(f0, f1, _layer_weights(tf), tcfg["layer_names"], tcfg["nhead"], m0, m1)
+    g0, g1 = tf(_t(f0), _t(f1), None if m0 is None else _t(m0), None if m1 is None else _t(m1))
+    for g, o in ((g0, o0), (g1, o1)):
+        err = np.abs(g.cpu().numpy() - o).max()
+        assert err < 2e-4, f"{cfgname}: transformer output differs by {err:.3e}"
+
+
+# ------------------------------------------------------------------------------------------------ coarse matching
+@pytest.mark.parametrize("case", CM_CASES, ids=[c["name"] for c in CM_CASES])
+def test_coarse_matching_matches_reference_golden(case):
+    import loftr_b200.loftr as L
+    gold = util.load_golden(case["name"])
+    cfg = build_cfg(case)["match_coarse"]
+    inp = build_cm_inputs(case)
+    mod = L.CoarseMatching(cfg).eval().to(DEV)
+    if cfg["match_type"] == "sinkhorn":
+        mod.bin_score.data = torch.tensor(float(case.get("bin_score", 1.0)), device=DEV)
+    (h0, w0), (h1, w1) = case["hw0c"], case["hw1c"]
+    data = {"hw0_i": (h0 * 8, w0 * 8), "hw1_i": (h1 * 8, w1 * 8), "hw0_c": (h0, w0), "hw1_c": (h1, w1)}
+    m0 = m1 = None
+    if "mask0" in inp:
+        data["mask0"], data["mask1"] = _t(inp["mask0"]), _t(inp["mask1"])
+        m0, m1 = data["mask0"].flatten(-2), data["mask1"].flatten(-2)
+    mod(_t(inp["feat_c0"]), _t(inp["feat_c1"]), data, m0, m1)
+    got = {k: data[k].cpu().numpy() for k in ["b_ids", "i_ids", "j_ids", "mconf", "mkpts0_c", "mkpts1_c"]}
+    stats = util.compare_matches(got, gold, gold, conf_rtol=1e-3, px_tol=1e-3, min_overlap=1.0, label=case["name"])
+    assert stats["n"] == len(gold["b_ids"])
+    assert data["b_ids"].dtype == torch.int64 and data["mconf"].dtype == torch.float32
+
+
+def test_coarse_matching_full_size_vs_oracle():
+    """640x480 grid (L = S = 4800, 38 row tiles, partial last tile), 2 pairs, dual-softmax, thr 0."""
+    import loftr_b200.loftr as L
+    rs = np.random.RandomState(5)
+    n, h, w, c = 2, 60, 80, 256
+    base = rs.standard_normal((n, h * w, c)).astype(np.float32)
+    f0 = base * 1.2 + 3.0   # large common-mode part like the real features (SURVEY.md §7 hard part 1)
+    perm = rs.permutation(h * w)
+    f1 = (base[:, perm] * 1.2 + 3.0 + 0.3 * rs.standard_normal((n, h * w, c))).astype(np.float32)
+    cfg = build_cfg({"thr": 0.0})["match_coarse"]
+    out = O.coarse_matching(f0, f1, cfg, (480, 640), (h, w), (h, w))
+    mod = L.CoarseMatching(cfg).eval()
+    data = {"hw0_i": (480, 640), "hw1_i": (480, 640), "hw0_c": (h, w), "hw1_c": (h, w)}
+    mod(_t(f0), _t(f1), data)
+    got = {k: data[k].cpu().numpy() for k in ["b_ids", "i_ids", "j_ids", "mconf", "mkpts0_c", "mkpts1_c"]}
+    assert len(out["b_ids"]) > 1000
+    stats = util.compare_matches(got, out, None, conf_rtol=1e-3, px_tol=1e-3, min_overlap=0.995, label="full")
+    assert stats["n"] > 1000
+
+
+# ------------------------------------------------------------------------------------------------ fine level
+def test_fine_level_matches_oracle():
+    case = CASES[0]
+    model, cfg, state = util.build_model(case, DEV)
+    rs = np.random.RandomState(9)
+    n, hc, wc = 2, 12, 16
+    hf, wf = hc * 4, wc * 4
+    feat_f0 = rs.standard_normal((n, 128, hf, wf)).astype(np.float32)
+    feat_f1 = rs.standard_normal((n, 128, hf, wf)).astype(np.float32)
+    feat_c0 = rs.standard_normal((n, hc * wc, 256)).astype(np.float32)
+    feat_c1 = rs.standard_normal((n, hc * wc, 256)).astype(np.float32)
+    m = 50
+    b_ids = np.sort(rs.randint(0, n, m)).astype(np.int64)
+    i_ids = rs.randint(0, hc * wc, m).astype(np.int64)   # includes border cells -> zero padding of windows
+    j_ids = rs.randint(0, hc * wc, m).astype(np.int64)
+    i_ids[0], j_ids[0] = 0, hc * wc - 1
+    fw = {k: state[f"fine_preprocess.{k}"] for k in ["down_proj.weight", "down_proj.bias", "merge_feat.weight",
+                                                      "merge_feat.bias"]}
+    o0, o1 = O.fine_preprocess(feat_f0, feat_f1, feat_c0, feat_c1, b_ids, i_ids, j_ids, wc, wc, 5, 4, fw)
+    data = {"hw0_i": (hc * 8, wc * 8), "hw0_c": (hc, wc), "hw1_c": (hc, wc), "hw0_f": (hf, wf), "hw1_f": (hf, wf),
+            "b_ids": _t(b_ids), "i_ids": _t(i_ids), "j_ids": _t(j_ids)}
+    for layout in ("nchw", "nhwc"):
+        tf0, tf1 = _t(feat_f0), _t(feat_f1)
+        if layout == "nhwc":
+            tf0, tf1 = tf0.contiguous(memory_format=torch.channels_last), tf1.contiguous(memory_format=torch.channels_last)
+        g0, g1 = model.fine_preprocess(tf0, tf1, _t(feat_c0), _t(feat_c1), data)
+        assert np.abs(g0.cpu().numpy() - o0).max() < 2e-4, layout
+        assert np.abs(g1.cpu().numpy() - o1).max() < 2e-4, layout
+    # fine matching on the oracle's transformer output
+    mk0 = rs.uniform(0, 100, (m, 2)).astype(np.float32)
+    mk1 = rs.uniform(0, 100, (m, 2)).astype(np.float32)
+    scale1 = rs.uniform(1, 2, (n, 2)).astype(np.float32)
+    of = O.fine_matching(o0, o1, mk0, mk1, b_ids, (hc * 8, wc * 8), (hf, wf), scale1)
+    data.update({"mkpts0_c": _t(mk0), "mkpts1_c": _t(mk1), "scale0": _t(scale1), "scale1": _t(scale1),
+                 "mconf": torch.ones(m, device=DEV)})
+    model.fine_matching(_t(o0), _t(o1), data)
+    np.testing.assert_allclose(data["expec_f"].cpu().numpy(), of["expec_f"], atol=2e-5)
+    np.testing.assert_allclose(data["mkpts1_f"].cpu().numpy(), of["mkpts1_f"], atol=2e-4)
+    assert data["mkpts0_f"] is data["mkpts0_c"]   # the reference aliases them (fine_matching.py:67)
+
+
+# ------------------------------------------------------------------------------------------------ end to end
+def _run_engine(case):
+    model, cfg, state = util.build_model(case, DEV)
+    inp = build_inputs(case)
+    data = {k: _t(v) for k, v in inp.items()}
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model(data)
+    return model, data
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_end_to_end_matches_reference_golden(case):
+    gold = util.load_golden(case["name"])
+    _, data = _run_engine(case)
+    for k in ["hw0_i", "hw1_i", "hw0_c", "hw1_c", "hw0_f", "hw1_f"]:
+        assert tuple(data[k]) == tuple(gold[k])
+    assert data["bs"] == case["n"] and data["W"] == 5
+    got = {k: data[k].cpu().numpy() for k in ["b_ids", "i_ids", "j_ids", "mconf", "mkpts0_c", "mkpts1_c", "mkpts0_f",
+                                              "mkpts1_f", "expec_f"]}
+    np.testing.assert_allclose(data["_feat_c0"].cpu().numpy()[:, ::7, ::5], gold["feat_c0_s"], rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(data["_feat_c1"].cpu().numpy()[:, ::7, ::5], gold["feat_c1_s"], rtol=1e-3, atol=1e-3)
+    stats = util.compare_matches(got, gold, gold, conf_rtol=1e-3, px_tol=0.5, min_overlap=0.97, label=case["name"])
+    m = len(gold["b_ids"])
+    if m == 0:
+        assert got["b_ids"].shape == (0,) and got["mkpts0_f"].shape == (0, 2) and got["expec_f"].shape == (0, 3)
+        assert data["mkpts0_f"] is data["mkpts0_c"]
+    else:
+        assert stats["n"] >= 0.97 * m
+    assert got["mkpts1_f"].dtype == np.float32 and data["m_bids"].dtype == torch.int64
+    assert data["gt_mask"].dtype == torch.bool and data["gt_mask"].shape[0] == len(got["b_ids"])
+
+
+def test_end_to_end_640x480_vs_oracle():
+    """Config 1/2 of BASELINE.json (640x480, indoor_ds) at thr 0: engine vs oracle on the SAME backbone features."""
+    case = {"name": "full", "n": 1, "hw0": (480, 640), "hw1": (480, 640), "thr": 0.0, "images": "smooth"}
+    model, data = _run_engine(case)
+    out = util.oracle_forward(case, backbone_device=DEV)
+    got = {k: data[k].cpu().numpy() for k in ["b_ids", "i_ids", "j_ids", "mconf", "mkpts0_c", "mkpts1_c", "mkpts0_f",
+                                              "mkpts1_f"]}
+    assert len(out["b_ids"]) > 300
+    stats = util.compare_matches(got, out, None, conf_rtol=1e-3, px_tol=0.5, min_overlap=0.99, label="640x480")
+    err = np.abs(data["_feat_c0"].cpu().numpy() - out["feat_c0"]).max()
+    assert err < 1e-3, f"coarse transformer output differs by {err:.3e}"
+    print("640x480 parity:", stats)
+
+
+def test_no_cpu_fallback():
+    import loftr_b200
+    model = loftr_b200.LoFTR(loftr_b200.get_cfg("indoor_ds")).eval()
+    with pytest.raises(RuntimeError):
+        model({"image0": torch.rand(1, 1, 64, 64), "image1": torch.rand(1, 1, 64, 64)})

@@ -1,0 +1,96 @@
+"""CPU-side tests: C-ABI surface, config / state_dict compatibility, error behaviour of the drop-in API."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import loftr_b200
+from loftr_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "loftr_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(lb_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/loftr_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes binding and header disagree"
+    assert _lib.load().lb_version() >= 100
+
+
+def test_struct_layouts_match_header_field_order():
+    header = open(os.path.join(ROOT, "include", "loftr_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    for cls in (_lib.LbEncoderLayerWeights, _lib.LbTransformerState, _lib.LbCoarseMatchArgs,
+                _lib.LbFinePreprocessArgs, _lib.LbFineMatchArgs):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cls.__name__, cls.__name__), header, re.S).group(1)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            first, *rest = decl.split(",")
+            names.append(re.findall(r"[A-Za-z_0-9]+", first)[-1])
+            names += [re.findall(r"[A-Za-z_0-9]+", r)[-1] for r in rest]
+        assert names == [f[0] for f in cls._fields_], cls.__name__
+
+
+def test_compute_without_gpu_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    model = loftr_b200.LoFTR(loftr_b200.get_cfg("indoor_ds")).eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model({"image0": torch.rand(1, 1, 64, 64), "image1": torch.rand(1, 1, 64, 64)})
+    # and the library itself refuses as well (no device)
+    lib = _lib.load()
+    assert lib.lb_split_planes(None, 4, 4, 4, None, None, 4, 0, None) != 0
+    assert b"" != lib.lb_last_error()
+
+
+def test_default_cfg_matches_reference_schema():
+    d = loftr_b200.default_cfg
+    assert d["coarse"]["temp_bug_fix"] is False and d["match_coarse"]["skh_prefilter"] is True
+    assert "sparse_spvs" not in d["match_coarse"]
+    c = loftr_b200.get_cfg("indoor_ot")
+    assert c["match_coarse"]["match_type"] == "sinkhorn" and c["coarse"]["temp_bug_fix"] is True
+    assert loftr_b200.get_cfg("outdoor_ds")["match_coarse"]["thr"] == 0.2
+
+
+def test_state_dict_names_and_matcher_prefix():
+    cfg = loftr_b200.get_cfg("indoor_ot")
+    m = loftr_b200.LoFTR(cfg).eval()
+    sd = m.state_dict()
+    assert len(sd) == 212 and "coarse_matching.bin_score" in sd      # 211 + bin_score
+    assert "pos_encoding.pe" not in sd                               # non-persistent buffer
+    assert sd["loftr_coarse.layers.7.mlp.0.weight"].shape == (512, 512)
+    assert sd["fine_preprocess.merge_feat.weight"].shape == (128, 256)
+    assert sum(p.numel() for p in loftr_b200.LoFTR(loftr_b200.get_cfg("indoor_ds")).parameters()) == 11561456
+    prefixed = {"matcher." + k: v.clone() for k, v in sd.items()}
+    m2 = loftr_b200.LoFTR(cfg)
+    m2.load_state_dict(prefixed)
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+
+
+def test_training_mode_is_rejected():
+    m = loftr_b200.LoFTR(loftr_b200.get_cfg("indoor_ds")).train()
+    with pytest.raises(NotImplementedError):
+        m({"image0": torch.rand(1, 1, 64, 64), "image1": torch.rand(1, 1, 64, 64)})
+
+
+def test_backbone_16_4_variant_builds():
+    cfg = loftr_b200.get_cfg("indoor_ds")
+    cfg["resolution"] = (16, 4)
+    cfg["resnetfpn"]["block_dims"] = [128, 196, 256, 512]
+    from loftr_b200.backbone import build_backbone
+    bb = build_backbone(cfg).eval()
+    with torch.no_grad():
+        c, f = bb(torch.rand(1, 1, 64, 96))
+    assert c.shape == (1, 512, 4, 6) and f.shape == (1, 196, 16, 24)
+    assert "layer4_outconv.weight" in bb.state_dict() and "layer2_outconv2.3.weight" in bb.state_dict()
