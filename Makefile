@@ -6,7 +6,7 @@ LIB       := loftr_b200/lib/libloftr_b200.so
 CSRC      := loftr_b200/csrc
 HDRS      := $(wildcard $(CSRC)/*.cuh) include/loftr_b200.h
 
-all: $(LIB) build/bringup oracle
+all: $(LIB) build/bringup
 
 $(LIB): $(CSRC)/engine.cu $(HDRS)
 	@mkdir -p loftr_b200/lib
@@ -16,10 +16,7 @@ build/bringup: tests/cuda/bringup.cu $(LIB)
 	@mkdir -p build
 	$(NVCC) $(ARCH) -O2 -std=c++17 tests/cuda/bringup.cu -o $@ -Lloftr_b200/lib -lloftr_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../loftr_b200/lib'
 
-oracle:
-	$(MAKE) -C oracle
-
 clean:
-	rm -rf build loftr_b200/lib oracle/_build
+	rm -rf build loftr_b200/lib
 
-.PHONY: all oracle clean
+.PHONY: all clean

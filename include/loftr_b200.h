@@ -44,6 +44,15 @@ const char* lb_last_error(void);
 /* number of kernels this library has launched in this process (for bench.py's gpu_launches) */
 long long lb_launch_count(void);
 
+/* Optional per-launch CUDA-event timing of the tensor-core kernels (events recorded on the launching
+ * stream around each kernel while enabled).  lb_timing_enable(1) clears old records and starts recording,
+ * lb_timing_collect synchronises the recorded events and returns per-tag total milliseconds and launch counts
+ * (arrays of lb_timing_num_tags() entries; names via lb_timing_tag_name). */
+int lb_timing_enable(int on);
+int lb_timing_num_tags(void);
+const char* lb_timing_tag_name(int tag);
+int lb_timing_collect(double* total_ms /*host*/, long long* counts /*host*/, int n);
+
 /* fp32 [rows, cols] (row stride ld_x) -> fp16 planes written at column offset col0 of [rows, ld_pl] buffers. */
 int lb_split_planes(const float* x, long rows, int cols, int ld_x, void* hi, void* lo, int ld_pl, int col0,
                     void* stream);
@@ -139,10 +148,10 @@ typedef struct LbFinePreprocessArgs {
   const long long* b_ids;
   const long long* i_ids;
   const long long* j_ids;
-  const float* down_w;    /* fine_preprocess.down_proj.weight [Cf, Cc], bias [Cf] */
+  const float* down_wt;   /* fine_preprocess.down_proj.weight TRANSPOSED [Cc, Cf], bias [Cf] */
   const float* down_b;
-  const float* merge_w;   /* fine_preprocess.merge_feat.weight [Cf, 2Cf] (fp32) */
-  const float* merge_b;
+  const float* merge_w2t; /* fine_preprocess.merge_feat.weight[:, Cf:2Cf] TRANSPOSED [Cf, Cf] (fp32) */
+  const float* merge_b;   /* fine_preprocess.merge_feat.bias [Cf] */
   const void* merge_w_hi; /* planes of merge_w[:, 0:Cf]  -> [Cf, Cf] */
   const void* merge_w_lo;
   /* outputs: fine transformer state, rows = side*M*W*W + m*W*W + k */

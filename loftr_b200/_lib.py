@@ -59,7 +59,7 @@ class LbFinePreprocessArgs(C.Structure):
         ("w0c", c_int), ("w1c", c_int), ("stride", c_int), ("W", c_int), ("Cf", c_int), ("Cc", c_int),
         ("feat_c", c_void_p), ("n_pairs", c_int), ("L", c_int), ("S", c_int), ("M", c_long),
         ("b_ids", c_void_p), ("i_ids", c_void_p), ("j_ids", c_void_p),
-        ("down_w", c_void_p), ("down_b", c_void_p), ("merge_w", c_void_p), ("merge_b", c_void_p),
+        ("down_wt", c_void_p), ("down_b", c_void_p), ("merge_w2t", c_void_p), ("merge_b", c_void_p),
         ("merge_w_hi", c_void_p), ("merge_w_lo", c_void_p),
         ("x_f32", c_void_p), ("cat_hi", c_void_p), ("cat_lo", c_void_p),
     ]
@@ -78,6 +78,10 @@ SIGNATURES = {
     "lb_version": (c_int, []),
     "lb_last_error": (C.c_char_p, []),
     "lb_launch_count": (C.c_longlong, []),
+    "lb_timing_enable": (c_int, [c_int]),
+    "lb_timing_num_tags": (c_int, []),
+    "lb_timing_tag_name": (C.c_char_p, [c_int]),
+    "lb_timing_collect": (c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong), c_int]),
     "lb_split_planes": (c_int, [c_void_p, c_long, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "lb_gemm_split": (c_int, [c_void_p, c_void_p, c_long, c_long, c_void_p, c_void_p, c_long, c_long, c_void_p,
                               c_long, c_long, c_int, c_int, c_int, c_int, c_void_p]),
@@ -128,3 +132,17 @@ def check(rc: int):
 def ptr(t):
     """Device pointer of a torch tensor (or None)."""
     return None if t is None else t.data_ptr()
+
+
+def timing_enable(on: bool):
+    check(load().lb_timing_enable(1 if on else 0))
+
+
+def timing_collect() -> dict:
+    """-> {tag: (total_ms, launches)} for every tensor-core kernel tag recorded since timing_enable(True)."""
+    lib = load()
+    n = lib.lb_timing_num_tags()
+    ms = (C.c_double * n)()
+    cnt = (C.c_longlong * n)()
+    check(lib.lb_timing_collect(ms, cnt, n))
+    return {lib.lb_timing_tag_name(i).decode(): (ms[i], cnt[i]) for i in range(n)}

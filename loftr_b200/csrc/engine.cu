@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "../../include/loftr_b200.h"
 #include "epilogues.cuh"
@@ -46,6 +47,21 @@ static int fail(const char* fmt, ...) {
     g_launches.fetch_add(1);          \
     LB_CUDA(cudaGetLastError());      \
   } while (0)
+
+// ------------------------------------------------------------------------------------------------ timing hook
+// Optional per-launch CUDA-event timing of the tensor-core kernels (bench.py's roofline leg): events are
+// recorded on the launching stream right around the kernel, and only while timing is enabled.
+enum Tag { TAG_GEMM_TEST = 0, TAG_PROJ, TAG_MERGE_LN, TAG_MLP1, TAG_MLP2_LN, TAG_SCORE_LSE, TAG_SCORE_ARGMAX,
+           TAG_FINE_MERGE, TAG_COUNT };
+static const char* kTagNames[TAG_COUNT] = {"gemm_test", "proj_act", "merge_ln", "mlp1_relu", "mlp2_ln_res",
+                                           "score_lse", "score_argmax", "fine_merge"};
+struct TimingRec {
+  cudaEvent_t e0, e1;
+  int tag;
+};
+static bool g_timing = false;
+static std::vector<TimingRec> g_recs;
+static std::mutex g_timing_mu;
 
 static int device_check(int* sm_count) {
   static std::once_flag once;
@@ -122,7 +138,7 @@ struct Planes {
 
 // ------------------------------------------------------------------------------------------------ GEMM launch
 template <int BN, class Epi>
-static int launch_gemm(const Planes& A, const Planes& B, int batches, int M, int N, int K, int n_chunks,
+static int launch_gemm(int tag, const Planes& A, const Planes& B, int batches, int M, int N, int K, int n_chunks,
                        const typename Epi::Params& ep, cudaStream_t st) {
   int sms = 0;
   LB_TRY(device_check(&sms));
@@ -158,15 +174,26 @@ static int launch_gemm(const Planes& A, const Planes& B, int batches, int M, int
   }
   const long items = static_cast<long>(batches) * s.m_tiles * s.n_chunks;
   const int grid = static_cast<int>(items < sms ? items : sms);
+  TimingRec rec{nullptr, nullptr, tag};
+  if (g_timing) {
+    LB_CUDA(cudaEventCreate(&rec.e0));
+    LB_CUDA(cudaEventCreate(&rec.e1));
+    LB_CUDA(cudaEventRecord(rec.e0, st));
+  }
   kern<<<grid, kGemmThreads, smem_bytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, s, ep);
   LB_LAUNCHED();
+  if (g_timing) {
+    LB_CUDA(cudaEventRecord(rec.e1, st));
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    g_recs.push_back(rec);
+  }
   return 0;
 }
 
 // number of n-chunks that gives every SM a few work items when a CTA must sweep many n tiles
 static int pick_chunks(int row_items, int n_tiles, int sms) {
   int c = 1;
-  while (static_cast<long>(row_items) * c < 4L * sms && c < n_tiles) ++c;
+  while (static_cast<long>(row_items) * c < 8L * sms && c < n_tiles) ++c;
   return c;
 }
 
@@ -246,17 +273,17 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
       Planes A{cat_hi + x_base * ldc, cat_lo + x_base * ldc, ldc, 0};
       Planes B{lw.wqkv_hi, lw.wqkv_lo, C, 0};
       typename Epi::Params ep{w.qkv + x_base * 3 * C, 3 * C, 2 * C, mask ? mask + x_base : nullptr, nullptr, 0};
-      LB_TRY((launch_gemm<BN, Epi>(A, B, 1, static_cast<int>(x_rows), 3 * C, C, 0, ep, stream)));
+      LB_TRY((launch_gemm<BN, Epi>(TAG_PROJ, A, B, 1, static_cast<int>(x_rows), 3 * C, C, 0, ep, stream)));
     } else {
       Planes Aq{cat_hi + x_base * ldc, cat_lo + x_base * ldc, ldc, 0};
       Planes Bq{lw.wqkv_hi, lw.wqkv_lo, C, 0};
       typename Epi::Params eq{w.qkv + x_base * 3 * C, 3 * C, C, mask ? mask + x_base : nullptr, nullptr, 0};
-      LB_TRY((launch_gemm<BN, Epi>(Aq, Bq, 1, static_cast<int>(x_rows), C, C, 0, eq, stream)));
+      LB_TRY((launch_gemm<BN, Epi>(TAG_PROJ, Aq, Bq, 1, static_cast<int>(x_rows), C, C, 0, eq, stream)));
       Planes Ak{cat_hi + s_base * ldc, cat_lo + s_base * ldc, ldc, 0};
       Planes Bk{static_cast<const __half*>(lw.wqkv_hi) + static_cast<long>(C) * C,
                 static_cast<const __half*>(lw.wqkv_lo) + static_cast<long>(C) * C, C, 0};
       typename Epi::Params ek{w.qkv + s_base * 3 * C + C, 3 * C, C, mask ? mask + s_base : nullptr, nullptr, 0};
-      LB_TRY((launch_gemm<BN, Epi>(Ak, Bk, 1, static_cast<int>(s_rows), 2 * C, C, 0, ek, stream)));
+      LB_TRY((launch_gemm<BN, Epi>(TAG_PROJ, Ak, Bk, 1, static_cast<int>(s_rows), 2 * C, C, 0, ek, stream)));
     }
   }
   // 2. KV = K^T V and Ksum per (source group, head)            [linear_attention.py:43-44]
@@ -295,7 +322,7 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
     typename Epi::Params ep{lw.ln1_g, lw.ln1_b, 1e-5f, nullptr, 0, nullptr, 0,
                             static_cast<__half*>(st.cat_hi) + x_base * ldc,
                             static_cast<__half*>(st.cat_lo) + x_base * ldc, static_cast<int>(ldc), C};
-    LB_TRY((launch_gemm<BN, Epi>(A, B, 1, static_cast<int>(x_rows), C, C, 0, ep, stream)));
+    LB_TRY((launch_gemm<BN, Epi>(TAG_MERGE_LN, A, B, 1, static_cast<int>(x_rows), C, C, 0, ep, stream)));
   }
   // 5. mlp[0] + ReLU on cat([x, message]) -> h planes           [transformer.py:55, mlp 22-26]
   {
@@ -304,7 +331,7 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
     Planes B{lw.w1_hi, lw.w1_lo, 2 * C, 0};
     typename Epi::Params ep{1, nullptr, 1, nullptr, 0, w.h_hi + x_base * ldc, w.h_lo + x_base * ldc,
                             static_cast<int>(ldc), 0};
-    LB_TRY((launch_gemm<BN, Epi>(A, B, 1, static_cast<int>(x_rows), 2 * C, 2 * C, 0, ep, stream)));
+    LB_TRY((launch_gemm<BN, Epi>(TAG_MLP1, A, B, 1, static_cast<int>(x_rows), 2 * C, 2 * C, 0, ep, stream)));
   }
   // 6. mlp[2] + norm2 + residual -> x_f32 and cat[:, 0:C]        [transformer.py:55-58]
   {
@@ -315,7 +342,7 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
     typename Epi::Params ep{lw.ln2_g, lw.ln2_b, 1e-5f, xf, C, xf, C,
                             static_cast<__half*>(st.cat_hi) + x_base * ldc,
                             static_cast<__half*>(st.cat_lo) + x_base * ldc, static_cast<int>(ldc), 0};
-    LB_TRY((launch_gemm<BN, Epi>(A, B, 1, static_cast<int>(x_rows), C, 2 * C, 0, ep, stream)));
+    LB_TRY((launch_gemm<BN, Epi>(TAG_MLP2_LN, A, B, 1, static_cast<int>(x_rows), C, 2 * C, 0, ep, stream)));
   }
   return 0;
 }
@@ -325,6 +352,36 @@ extern "C" {
 int lb_version(void) { return 100; }
 const char* lb_last_error(void) { return g_err; }
 long long lb_launch_count(void) { return g_launches.load(); }
+
+int lb_timing_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  for (auto& r : g_recs) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_recs.clear();
+  g_timing = on != 0;
+  return 0;
+}
+int lb_timing_num_tags(void) { return TAG_COUNT; }
+const char* lb_timing_tag_name(int tag) { return (tag >= 0 && tag < TAG_COUNT) ? kTagNames[tag] : ""; }
+int lb_timing_collect(double* total_ms, long long* counts, int n) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  for (int i = 0; i < n; ++i) {
+    total_ms[i] = 0.0;
+    counts[i] = 0;
+  }
+  for (auto& r : g_recs) {
+    LB_CUDA(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    LB_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    if (r.tag < n) {
+      total_ms[r.tag] += ms;
+      counts[r.tag] += 1;
+    }
+  }
+  return 0;
+}
 
 int lb_split_planes(const float* x, long rows, int cols, int ld_x, void* hi, void* lo, int ld_pl, int col0,
                     void* stream) {
@@ -351,11 +408,11 @@ int lb_gemm_split(const void* a_hi, const void* a_lo, long lda, long a_batch_str
   if (N % 256 == 0 || N > 128) {
     using Epi = EpiActStore<256>;
     Epi::Params ep{out, static_cast<int>(ldo), 0, nullptr, nullptr, 0};
-    return launch_gemm<256, Epi>(A, B, batches, M, N, K, 0, ep, st);
+    return launch_gemm<256, Epi>(TAG_GEMM_TEST, A, B, batches, M, N, K, 0, ep, st);
   }
   using Epi = EpiActStore<128>;
   Epi::Params ep{out, static_cast<int>(ldo), 0, nullptr, nullptr, 0};
-  return launch_gemm<128, Epi>(A, B, batches, M, N, K, 0, ep, st);
+  return launch_gemm<128, Epi>(TAG_GEMM_TEST, A, B, batches, M, N, K, 0, ep, st);
 }
 
 int lb_coarse_prep(const float* feat_nchw, const float* pe, int n_img, int C, int h, int w, int pe_h, int pe_w,
@@ -532,7 +589,7 @@ int lb_coarse_match(const LbCoarseMatchArgs* a, void* ws, size_t ws_bytes, void*
     }
     using Epi = EpiScoreLse<BN, true, true>;
     Epi::Params ep{scale, ct, rt, w.row_part, w.col_part};
-    LB_TRY((launch_gemm<BN, Epi>(A, B, n, L, S, C, chunks, ep, st)));
+    LB_TRY((launch_gemm<BN, Epi>(TAG_SCORE_LSE, A, B, n, L, S, C, chunks, ep, st)));
     // row_t = -rowLSE, col_t = -colLSE (kNegBig on padded entries)              [coarse_matching.py:119]
     lse_merge_kernel<<<cdiv(nl, TB), TB, 0, st>>>(w.row_part, n_chunks, nl, 0.f, nullptr, nullptr, L, a->mask0, w.row_t);
     LB_LAUNCHED();
@@ -559,7 +616,7 @@ int lb_coarse_match(const LbCoarseMatchArgs* a, void* ws, size_t ws_bytes, void*
       {
         using Epi = EpiScoreLse<BN, true, false>;
         Epi::Params ep{scale, w.col_t, nullptr, w.row_part, w.col_part};
-        LB_TRY((launch_gemm<BN, Epi>(A, B, n, L, S, C, chunks, ep, st)));
+        LB_TRY((launch_gemm<BN, Epi>(TAG_SCORE_LSE, A, B, n, L, S, C, chunks, ep, st)));
         lse_merge_kernel<<<cdiv(nl, TB), TB, 0, st>>>(w.row_part, n_chunks, nl, norm, a->bin_score, w.bin_v, L,
                                                       a->mask0, w.row_u);
         LB_LAUNCHED();
@@ -573,7 +630,7 @@ int lb_coarse_match(const LbCoarseMatchArgs* a, void* ws, size_t ws_bytes, void*
       {
         using Epi = EpiScoreLse<BN, false, true>;
         Epi::Params ep{scale, nullptr, w.row_t, w.row_part, w.col_part};
-        LB_TRY((launch_gemm<BN, Epi>(A, B, n, L, S, C, chunks, ep, st)));
+        LB_TRY((launch_gemm<BN, Epi>(TAG_SCORE_LSE, A, B, n, L, S, C, chunks, ep, st)));
         lse_merge_kernel<<<cdiv(ns, TB), TB, 0, st>>>(w.col_part, m_tiles, ns, norm, a->bin_score, w.bin_u, S,
                                                       a->mask1, w.col_v);
         LB_LAUNCHED();
@@ -597,7 +654,7 @@ int lb_coarse_match(const LbCoarseMatchArgs* a, void* ws, size_t ws_bytes, void*
   for (int pass = 0; pass < passes; ++pass) {
     using Epi = EpiScoreArgmax<BN>;
     Epi::Params ep{scale, alpha, w.col_t, w.row_t, w.row_apart, w.col_apart};
-    LB_TRY((launch_gemm<BN, Epi>(A, B, n, L, S, C, chunks, ep, st)));
+    LB_TRY((launch_gemm<BN, Epi>(TAG_SCORE_ARGMAX, A, B, n, L, S, C, chunks, ep, st)));
     argmax_merge_kernel<<<cdiv(nl, TB), TB, 0, st>>>(w.row_apart, n_chunks, nl, w.row_key, w.row_arg);
     LB_LAUNCHED();
     argmax_merge_kernel<<<cdiv(ns, TB), TB, 0, st>>>(w.col_apart, m_tiles, ns, w.col_key, w.col_arg);
@@ -685,9 +742,9 @@ int lb_fine_preprocess(const LbFinePreprocessArgs* a, void* ws, size_t ws_bytes,
   fb.set1_row_base = static_cast<long>(a->n_pairs) * a->L;
   fb.L = a->L; fb.S = a->S; fb.Cc = a->Cc; fb.Cf = a->Cf; fb.M = a->M;
   fb.b_ids = a->b_ids; fb.i_ids = a->i_ids; fb.j_ids = a->j_ids;
-  fb.Wd = a->down_w; fb.bd = a->down_b; fb.Wm = a->merge_w; fb.bm = a->merge_b;
+  fb.WdT = a->down_wt; fb.bd = a->down_b; fb.Wm2T = a->merge_w2t; fb.bm = a->merge_b;
   fb.gbias = gbias;
-  fine_bias_kernel<<<static_cast<unsigned>(2 * a->M), 128, 0, st>>>(fb);
+  fine_bias_kernel<<<static_cast<unsigned>(cdiv(2 * a->M, kFineBiasWin)), 128, 0, st>>>(fb);
   LB_LAUNCHED();
 
   // merge_feat over [window | coarse] = window @ Wm[:, :Cf]^T + per-window bias     [fine_preprocess.py:52-56]
@@ -696,7 +753,7 @@ int lb_fine_preprocess(const LbFinePreprocessArgs* a, void* ws, size_t ws_bytes,
   Planes B{a->merge_w_hi, a->merge_w_lo, a->Cf, 0};
   Epi::Params ep{0, gbias, WW, a->x_f32, a->Cf, static_cast<__half*>(a->cat_hi), static_cast<__half*>(a->cat_lo),
                  2 * a->Cf, 0};
-  return launch_gemm<128, Epi>(A, B, 1, static_cast<int>(rows), a->Cf, a->Cf, 0, ep, st);
+  return launch_gemm<128, Epi>(TAG_FINE_MERGE, A, B, 1, static_cast<int>(rows), a->Cf, a->Cf, 0, ep, st);
 }
 
 int lb_fine_match(const LbFineMatchArgs* a, void* stream) {

@@ -18,8 +18,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // exp(x) for x <= 0 (softmax numerators)
 __device__ __forceinline__ float exp_fast(float x) { return ex2_approx(x * kLog2e); }
 
-__device__ __forceinline__ int epi_tid() { return threadIdx.x - kEpiWarp0 * 32; }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ int epi_tid() { return threadIdx.x - kEpiWarp0 * 32; }   // 0..255
+__device__ __forceinline__ int epi_row() { return epi_tid() & 127; }                  // accumulator row (TMEM lane)
+__device__ __forceinline__ int epi_half() { return epi_tid() >> 7; }                  // column half of the tile
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // x = hi + lo with both halves fp16 (round-to-nearest); |x| must stay below 65504.
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
@@ -55,7 +57,7 @@ __device__ __forceinline__ void store_f32x32(float* p, const float (&x)[32]) {
 
 __device__ __forceinline__ void load_acc32(uint32_t tmem_acc, int col, float (&x)[32]) {
   uint32_t v[32];
-  const uint32_t lane_base = static_cast<uint32_t>((epi_tid() >> 5) * 32) << 16;
+  const uint32_t lane_base = static_cast<uint32_t>(((epi_tid() >> 5) & 3) * 32) << 16;  // warp%4 owns 32 lanes
   tmem_ld32(tmem_acc + col + lane_base, v);
   tmem_ld_wait();
 #pragma unroll
@@ -83,13 +85,14 @@ struct EpiActStore {
   __device__ void item_begin(int, int, int) {}
   __device__ void item_end(int, int, int) {}
   __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
-    const int r = m0 + epi_tid();
+    const int r = m0 + epi_row();
     const bool row_ok = r < s.M;
     const long grow = static_cast<long>(batch) * s.M + r;
     float mk = 1.f;
     if (row_ok && p.rowmask) mk = p.rowmask[grow] ? 1.f : 0.f;
+    const int c_begin = epi_half() * (BLOCK_N / 64);
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
+    for (int c = c_begin; c < c_begin + BLOCK_N / 64; ++c) {
       const int col = n0 + c * 32;
       if (col >= s.N) break;  // warp-uniform
       float x[32];
@@ -123,14 +126,16 @@ struct EpiLayerNorm {
     int ld_pl;
     int pl_col0;
   };
-  static constexpr int kSmemBytes = 2 * BLOCK_N * 4;
+  static constexpr int kSmemBytes = 2 * BLOCK_N * 4 + 2 * 128 * 4;
   const Params& p;
   const GemmShape& s;
   float* sg;
   float* sb;
+  float* s_red;  // [2 halves][128 rows]
   __device__ EpiLayerNorm(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_) {
     sg = reinterpret_cast<float*>(smem);
     sb = sg + BLOCK_N;
+    s_red = sb + BLOCK_N;
     for (int i = epi_tid(); i < BLOCK_N; i += kEpiThreads) {
       sg[i] = p.gamma[i];
       sb[i] = p.beta[i];
@@ -139,22 +144,33 @@ struct EpiLayerNorm {
   }
   __device__ void item_begin(int, int, int) {}
   __device__ void item_end(int, int, int) {}
+  // the two threads that share a row (column halves) exchange their partial sums through smem
+  __device__ float row_total(float part) {
+    const int row = epi_row(), half = epi_half();
+    s_red[half * 128 + row] = part;
+    epi_bar_sync();
+    const float tot = s_red[row] + s_red[128 + row];
+    epi_bar_sync();
+    return tot;
+  }
   __device__ void tile(uint32_t tmem_acc, int batch, int m0, int) {
-    const int r = m0 + epi_tid();
+    const int r = m0 + epi_row();
     const bool row_ok = r < s.M;
     const long grow = static_cast<long>(batch) * s.M + r;
+    const int c_begin = epi_half() * (BLOCK_N / 64);
+    const int c_end = c_begin + BLOCK_N / 64;
     float sum = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
       float x[32];
       load_acc32(tmem_acc, c * 32, x);
 #pragma unroll
       for (int j = 0; j < 32; ++j) sum += x[j];
     }
-    const float mean = sum * (1.f / BLOCK_N);
+    const float mean = row_total(sum) * (1.f / BLOCK_N);
     float sq = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
       float x[32];
       load_acc32(tmem_acc, c * 32, x);
 #pragma unroll
@@ -163,9 +179,9 @@ struct EpiLayerNorm {
         sq += d * d;
       }
     }
-    const float rstd = rsqrtf(sq * (1.f / BLOCK_N) + p.eps);
+    const float rstd = rsqrtf(row_total(sq) * (1.f / BLOCK_N) + p.eps);
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
       float x[32];
       load_acc32(tmem_acc, c * 32, x);
 #pragma unroll
@@ -217,13 +233,14 @@ struct EpiPlanes {
   __device__ void item_begin(int, int, int) {}
   __device__ void item_end(int, int, int) {}
   __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
-    const int r = m0 + epi_tid();
+    const int r = m0 + epi_row();
     const bool row_ok = r < s.M;
     const long grow = static_cast<long>(batch) * s.M + r;
     const float* gb = nullptr;
     if (p.gbias && row_ok) gb = p.gbias + (grow / p.group_rows) * s.N;
+    const int c_begin = epi_half() * (BLOCK_N / 64);
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
+    for (int c = c_begin; c < c_begin + BLOCK_N / 64; ++c) {
       const int col = n0 + c * 32;
       if (col >= s.N) break;
       float x[32];
@@ -309,19 +326,21 @@ struct EpiScoreLse {
     float2* row_part;       // [n_chunks][batches*M]
     float2* col_part;       // [m_tiles][batches*N]
   };
-  // colterm staging + per-warp column partials + per-warp column-max broadcast
-  static constexpr int kSmemBytes = BLOCK_N * 4 + 4 * BLOCK_N * 8 + 4 * 32 * 4;
+  // colterm staging + per-warp-row-quarter column partials + per-warp column-max broadcast + row merge
+  static constexpr int kSmemBytes = BLOCK_N * 4 + 4 * BLOCK_N * 8 + 8 * 32 * 4 + 128 * 8;
   const Params& p;
   const GemmShape& s;
   float* s_ct;       // [BLOCK_N]
   float2* s_cpart;   // [4][BLOCK_N]
-  float* s_cmax;     // [4][32]
+  float* s_cmax;     // [8][32]
+  float2* s_rmerge;  // [128]
   float row_m, row_l;
 
   __device__ EpiScoreLse(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_) {
     s_ct = reinterpret_cast<float*>(smem);
     s_cpart = reinterpret_cast<float2*>(smem + BLOCK_N * 4);
     s_cmax = reinterpret_cast<float*>(smem + BLOCK_N * 4 + 4 * BLOCK_N * 8);
+    s_rmerge = reinterpret_cast<float2*>(smem + BLOCK_N * 4 + 4 * BLOCK_N * 8 + 8 * 32 * 4);
   }
   __device__ void item_begin(int, int, int) {
     row_m = kNegBig;
@@ -329,18 +348,29 @@ struct EpiScoreLse {
   }
   __device__ void item_end(int batch, int m0, int chunk) {
     if (kRows) {
-      const int r = m0 + epi_tid();
-      if (r < s.M) {
-        p.row_part[static_cast<long>(chunk) * s.batches * s.M + static_cast<long>(batch) * s.M + r] =
-            make_float2(row_m, row_l);
+      // merge the two column halves of each row, then one thread per row writes the partial
+      const int row = epi_row();
+      if (epi_half() == 1) s_rmerge[row] = make_float2(row_m, row_l);
+      epi_bar_sync();
+      if (epi_half() == 0) {
+        const float2 o = s_rmerge[row];
+        const float m = fmaxf(row_m, o.x);
+        const float l = row_l * exp_fast(row_m - m) + o.y * exp_fast(o.x - m);
+        const int r = m0 + row;
+        if (r < s.M) {
+          p.row_part[static_cast<long>(chunk) * s.batches * s.M + static_cast<long>(batch) * s.M + r] =
+              make_float2(m, l);
+        }
       }
+      epi_bar_sync();
     }
   }
   __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
     const int t = epi_tid();
-    const int w = t >> 5;
+    const int w = t >> 5;        // 0..7
+    const int q = w & 3;         // row quarter
     const int lane = t & 31;
-    const int r = m0 + t;
+    const int r = m0 + epi_row();
     // stage column terms of this tile
     for (int j = t; j < BLOCK_N; j += kEpiThreads) {
       const int col = n0 + j;
@@ -352,8 +382,9 @@ struct EpiScoreLse {
     if (r < s.M) rt = p.rowterm ? p.rowterm[static_cast<long>(batch) * s.M + r] : 0.f;
     epi_bar_sync();
 
+    const int c_begin = epi_half() * (BLOCK_N / 64);
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
+    for (int c = c_begin; c < c_begin + BLOCK_N / 64; ++c) {
       if (n0 + c * 32 >= s.N) break;
       float z[32];
       load_acc32(tmem_acc, c * 32, z);
@@ -361,35 +392,31 @@ struct EpiScoreLse {
       for (int j = 0; j < 32; ++j) z[j] *= p.scale;
 
       if (kRows) {
-        float x[32];
         float cm = kNegBig;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          x[j] = z[j] + s_ct[c * 32 + j];
-          cm = fmaxf(cm, x[j]);
-        }
+        for (int j = 0; j < 32; ++j) cm = fmaxf(cm, z[j] + s_ct[c * 32 + j]);
         const float m_new = fmaxf(row_m, cm);
         float acc = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc += exp_fast(x[j] - m_new);
+        for (int j = 0; j < 32; ++j) acc += exp_fast(z[j] + s_ct[c * 32 + j] - m_new);
         row_l = row_l * exp_fast(row_m - m_new) + acc;
         row_m = m_new;
       }
       if (kCols) {
-        float y[32], v[32];
+        float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          y[j] = z[j] + rt;
-          v[j] = y[j];
+          z[j] += rt;
+          v[j] = z[j];
         }
         const float cmax = warp_transpose_reduce(v, OpMaxF());  // lane j: max of column c*32+j
         s_cmax[w * 32 + lane] = cmax;
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = exp_fast(y[j] - s_cmax[w * 32 + j]);
+        for (int j = 0; j < 32; ++j) v[j] = exp_fast(z[j] - s_cmax[w * 32 + j]);
         __syncwarp();
         const float csum = warp_transpose_reduce(v, OpAddF());
-        s_cpart[w * BLOCK_N + c * 32 + lane] = make_float2(cmax, csum);
+        s_cpart[q * BLOCK_N + c * 32 + lane] = make_float2(cmax, csum);
       }
     }
     if (kCols) {
@@ -400,11 +427,11 @@ struct EpiScoreLse {
         if (col < s.N) {
           float m = kNegBig;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) m = fmaxf(m, s_cpart[q * BLOCK_N + j].x);
+          for (int qq = 0; qq < 4; ++qq) m = fmaxf(m, s_cpart[qq * BLOCK_N + j].x);
           float l = 0.f;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 pq = s_cpart[q * BLOCK_N + j];
+          for (int qq = 0; qq < 4; ++qq) {
+            const float2 pq = s_cpart[qq * BLOCK_N + j];
             l += pq.y * exp_fast(pq.x - m);
           }
           p.col_part[static_cast<long>(m0 / kBlockM) * s.batches * s.N + static_cast<long>(batch) * s.N + col] =
@@ -437,36 +464,49 @@ struct EpiScoreArgmax {
     ArgPart* row_part;     // [n_chunks][batches*M]
     ArgPart* col_part;     // [m_tiles][batches*N]
   };
-  static constexpr int kSmemBytes = BLOCK_N * 4 + 4 * BLOCK_N * 8;
+  static constexpr int kSmemBytes = BLOCK_N * 4 + 4 * BLOCK_N * 8 + 128 * 8;
   const Params& p;
   const GemmShape& s;
   float* s_ct;
   unsigned long long* s_cpart;  // [4][BLOCK_N]
+  ArgPart* s_rmerge;            // [128]
   float best_key;
   int best_j;
 
   __device__ EpiScoreArgmax(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_) {
     s_ct = reinterpret_cast<float*>(smem);
     s_cpart = reinterpret_cast<unsigned long long*>(smem + BLOCK_N * 4);
+    s_rmerge = reinterpret_cast<ArgPart*>(smem + BLOCK_N * 4 + 4 * BLOCK_N * 8);
   }
   __device__ void item_begin(int, int, int) {
     best_key = -3.0e38f;
     best_j = -1;
   }
   __device__ void item_end(int batch, int m0, int chunk) {
-    const int r = m0 + epi_tid();
-    if (r < s.M) {
+    const int row = epi_row();
+    if (epi_half() == 1) {
       ArgPart a;
       a.key = best_key;
       a.idx = best_j;
-      p.row_part[static_cast<long>(chunk) * s.batches * s.M + static_cast<long>(batch) * s.M + r] = a;
+      s_rmerge[row] = a;
     }
+    epi_bar_sync();
+    if (epi_half() == 0) {
+      ArgPart a;
+      a.key = best_key;
+      a.idx = best_j;
+      const ArgPart o = s_rmerge[row];      // right half = larger column indices: strict '>' keeps the first
+      if (o.key > a.key) a = o;
+      const int r = m0 + row;
+      if (r < s.M) p.row_part[static_cast<long>(chunk) * s.batches * s.M + static_cast<long>(batch) * s.M + r] = a;
+    }
+    epi_bar_sync();
   }
   __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
     const int t = epi_tid();
-    const int w = t >> 5;
+    const int q = (t >> 5) & 3;
     const int lane = t & 31;
-    const int r = m0 + t;
+    const int r = m0 + epi_row();
     for (int j = t; j < BLOCK_N; j += kEpiThreads) {
       const int col = n0 + j;
       s_ct[j] = (col < s.N) ? p.colterm[static_cast<long>(batch) * s.N + col] : kNegBig;
@@ -475,8 +515,9 @@ struct EpiScoreArgmax {
     const float sa = p.scale * p.alpha;
     epi_bar_sync();
 
+    const int c_begin = epi_half() * (BLOCK_N / 64);
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
+    for (int c = c_begin; c < c_begin + BLOCK_N / 64; ++c) {
       if (n0 + c * 32 >= s.N) break;
       float z[32];
       load_acc32(tmem_acc, c * 32, z);
@@ -499,7 +540,7 @@ struct EpiScoreArgmax {
         v[j] = (static_cast<unsigned long long>(f32_ordered(z[j] + rt)) << 32) | tag;
       }
       const unsigned long long best = warp_transpose_reduce(v, OpMaxU64());
-      s_cpart[w * BLOCK_N + c * 32 + lane] = best;
+      s_cpart[q * BLOCK_N + c * 32 + lane] = best;
     }
     epi_bar_sync();
     for (int j = t; j < BLOCK_N; j += kEpiThreads) {
@@ -507,8 +548,8 @@ struct EpiScoreArgmax {
       if (col < s.N) {
         unsigned long long b = s_cpart[j];
 #pragma unroll
-        for (int q = 1; q < 4; ++q) {
-          const unsigned long long o = s_cpart[q * BLOCK_N + j];
+        for (int qq = 1; qq < 4; ++qq) {
+          const unsigned long long o = s_cpart[qq * BLOCK_N + j];
           b = o > b ? o : b;
         }
         ArgPart a;

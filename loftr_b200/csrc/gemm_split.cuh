@@ -11,11 +11,12 @@
 // three tcgen05.mma (hi*hi + hi*lo + lo*hi) into one fp32 TMEM accumulator.  The dropped lo*lo term is
 // <= 2^-22 relative.
 //
-// Structure (one persistent CTA per SM, 256 threads):
-//   warp 0   : TMA producer    (global -> 128B-swizzled smem ring, 4 tiles per stage)
-//   warp 1   : MMA issuer      (one elected lane, tcgen05.mma cta_group::1, M=128, N=BLOCK_N, K=16)
-//   warp 2   : TMEM allocator
-//   warps 4-7: epilogue        (tcgen05.ld: thread t owns accumulator row t of the 128-row tile)
+// Structure (one persistent CTA per SM, 384 threads):
+//   warp 0    : TMA producer    (global -> 128B-swizzled smem ring, 4 tiles per stage)
+//   warp 1    : MMA issuer      (one elected lane, tcgen05.mma cta_group::1, M=128, N=BLOCK_N, K=16)
+//   warp 2    : TMEM allocator
+//   warps 4-11: epilogue        (tcgen05.ld: thread t owns accumulator row t%128 and the column half t/128;
+//                                two warps per SM sub-partition hide the TMEM / MUFU / shuffle latencies)
 // The fp32 accumulator is double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include "ptx.cuh"
@@ -25,8 +26,8 @@ namespace lb {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 fp16 = 128 bytes = one swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 256;
-constexpr int kEpiThreads = 128;
+constexpr int kGemmThreads = 384;
+constexpr int kEpiThreads = 256;  // two epilogue warpgroups: rows x {left, right} half of the tile's columns
 constexpr int kEpiWarp0 = 4;
 
 struct GemmShape {
@@ -51,7 +52,7 @@ struct GemmSmem {
   static constexpr int kBarBytes = 256;
 };
 
-// Epilogue contract (all methods are called by the 128 epilogue threads only):
+// Epilogue contract (all methods are called by the 256 epilogue threads only):
 //   struct Params;                               // trivially copyable, passed by value to the kernel
 //   static constexpr int kSmemBytes;             // extra dynamic smem the epilogue wants
 //   __device__ Epi(const Params&, uint8_t* smem, const GemmShape&);

@@ -544,6 +544,9 @@ __global__ void fine_gather_kernel(const FineGatherParams p) {
 // Per-window bias of the merge projection (reference fine_preprocess.py:50-56):
 //   c = down_proj(feat_c[b, idx]) ;  gbias = W_merge[:, Cf:2Cf] @ c + b_merge
 // (the repeated coarse half of the concatenation is identical for all WW positions of a window).
+// Weights arrive TRANSPOSED ([in, out]) so that thread o's reads are coalesced; a block handles
+// kFineBiasWin windows so every weight element is read once per kFineBiasWin outputs.
+constexpr int kFineBiasWin = 8;
 struct FineBiasParams {
   const float* feat_c;     // coarse transformer output x_f32 [rows, Cc]: set 0 rows then set 1 rows
   long set1_row_base;
@@ -552,35 +555,56 @@ struct FineBiasParams {
   const long long* b_ids;
   const long long* i_ids;
   const long long* j_ids;
-  const float* Wd;         // [Cf, Cc]
+  const float* WdT;        // [Cc, Cf]  down_proj.weight^T
   const float* bd;         // [Cf]
-  const float* Wm;         // [Cf, 2Cf]
+  const float* Wm2T;       // [Cf, Cf]  merge_feat.weight[:, Cf:2Cf]^T
   const float* bm;         // [Cf]
   float* gbias;            // [2M, Cf]
 };
 __global__ void __launch_bounds__(128) fine_bias_kernel(const FineBiasParams p) {
-  __shared__ float s_fc[256];
-  __shared__ float s_c[128];
-  const long win = blockIdx.x;
-  const int side = win >= p.M ? 1 : 0;
-  const long m = side ? win - p.M : win;
-  const long b = p.b_ids[m];
-  const long row = side ? p.set1_row_base + b * p.S + p.j_ids[m] : b * p.L + p.i_ids[m];
-  for (int c = threadIdx.x; c < p.Cc; c += blockDim.x) s_fc[c] = p.feat_c[row * p.Cc + c];
+  __shared__ float s_fc[kFineBiasWin][256];
+  __shared__ float s_c[kFineBiasWin][128];
+  const long win0 = static_cast<long>(blockIdx.x) * kFineBiasWin;
+  const long nwin = 2 * p.M;
+  for (int wv = 0; wv < kFineBiasWin; ++wv) {
+    const long win = win0 + wv;
+    if (win < nwin) {
+      const int side = win >= p.M ? 1 : 0;
+      const long m = side ? win - p.M : win;
+      const long b = p.b_ids[m];
+      const long row = side ? p.set1_row_base + b * p.S + p.j_ids[m] : b * p.L + p.i_ids[m];
+      for (int c = threadIdx.x; c < p.Cc; c += blockDim.x) s_fc[wv][c] = p.feat_c[row * p.Cc + c];
+    } else {
+      for (int c = threadIdx.x; c < p.Cc; c += blockDim.x) s_fc[wv][c] = 0.f;
+    }
+  }
   __syncthreads();
   const int o = threadIdx.x;
   if (o < p.Cf) {
-    float a = p.bd[o];
-    const float* wr = p.Wd + static_cast<long>(o) * p.Cc;
-    for (int c = 0; c < p.Cc; ++c) a = fmaf(wr[c], s_fc[c], a);
-    s_c[o] = a;
+    float a[kFineBiasWin];
+#pragma unroll
+    for (int wv = 0; wv < kFineBiasWin; ++wv) a[wv] = p.bd[o];
+    for (int c = 0; c < p.Cc; ++c) {
+      const float wgt = p.WdT[static_cast<long>(c) * p.Cf + o];
+#pragma unroll
+      for (int wv = 0; wv < kFineBiasWin; ++wv) a[wv] = fmaf(wgt, s_fc[wv][c], a[wv]);
+    }
+#pragma unroll
+    for (int wv = 0; wv < kFineBiasWin; ++wv) s_c[wv][o] = a[wv];
   }
   __syncthreads();
   if (o < p.Cf) {
-    float a = p.bm[o];
-    const float* wr = p.Wm + static_cast<long>(o) * (2 * p.Cf) + p.Cf;
-    for (int c = 0; c < p.Cf; ++c) a = fmaf(wr[c], s_c[c], a);
-    p.gbias[win * p.Cf + o] = a;
+    float a[kFineBiasWin];
+#pragma unroll
+    for (int wv = 0; wv < kFineBiasWin; ++wv) a[wv] = p.bm[o];
+    for (int c = 0; c < p.Cf; ++c) {
+      const float wgt = p.Wm2T[static_cast<long>(c) * p.Cf + o];
+#pragma unroll
+      for (int wv = 0; wv < kFineBiasWin; ++wv) a[wv] = fmaf(wgt, s_c[wv][c], a[wv]);
+    }
+#pragma unroll
+    for (int wv = 0; wv < kFineBiasWin; ++wv)
+      if (win0 + wv < nwin) p.gbias[(win0 + wv) * p.Cf + o] = a[wv];
   }
 }
 

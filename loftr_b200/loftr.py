@@ -288,9 +288,10 @@ class FinePreprocess(nn.Module):
             with torch.no_grad():
                 wm = self.merge_feat.weight.detach().float().contiguous()
                 hi, lo = split_planes(wm[:, : self.d_model_f].contiguous())
-                self._packed = {"wd": self.down_proj.weight.detach().float().contiguous(),
+                self._packed = {"wdt": self.down_proj.weight.detach().float().t().contiguous(),
                                 "bd": self.down_proj.bias.detach().float().contiguous(),
-                                "wm": wm, "bm": self.merge_feat.bias.detach().float().contiguous(),
+                                "wm2t": wm[:, self.d_model_f:].t().contiguous(),
+                                "bm": self.merge_feat.bias.detach().float().contiguous(),
                                 "wm_hi": hi, "wm_lo": lo}
             self._packed_key = key
         return self._packed
@@ -318,8 +319,8 @@ class FinePreprocess(nn.Module):
         a.stride, a.W, a.Cf, a.Cc = stride, W, cf, feat_c_all.shape[1]
         a.feat_c, a.n_pairs, a.L, a.S, a.M = feat_c_all.data_ptr(), n, L, S, m
         a.b_ids, a.i_ids, a.j_ids = data["b_ids"].data_ptr(), data["i_ids"].data_ptr(), data["j_ids"].data_ptr()
-        a.down_w, a.down_b, a.merge_w, a.merge_b = (p["wd"].data_ptr(), p["bd"].data_ptr(), p["wm"].data_ptr(),
-                                                    p["bm"].data_ptr())
+        a.down_wt, a.down_b, a.merge_w2t, a.merge_b = (p["wdt"].data_ptr(), p["bd"].data_ptr(), p["wm2t"].data_ptr(),
+                                                       p["bm"].data_ptr())
         a.merge_w_hi, a.merge_w_lo = p["wm_hi"].data_ptr(), p["wm_lo"].data_ptr()
         a.x_f32, a.cat_hi, a.cat_lo = state.x.data_ptr(), state.cat_hi.data_ptr(), state.cat_lo.data_ptr()
         nbytes = lib.lb_fine_preprocess_workspace_bytes(m, W, cf)

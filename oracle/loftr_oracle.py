@@ -14,11 +14,28 @@ All arrays are numpy float32 unless noted; shapes follow the reference docstring
 from __future__ import annotations
 
 import math
+import os
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
 F32 = np.float32
 INF = 1e9  # coarse_matching.py:6
+
+# numpy ufuncs release the GIL, so the big elementwise passes (softmax over L x S, LayerNorm, elu) are
+# row-blocked over a thread pool -- the reference's torch-CPU kernels use every host core too, and this
+# port is also the timed CPU baseline (bench.py).  Dense products go through BLAS (`@`).
+_POOL = ThreadPoolExecutor(max_workers=os.cpu_count() or 1)
+
+
+def _blocked(fn, n_rows, min_rows=64):
+    """Run fn(lo, hi) over row blocks [lo, hi) of an array with n_rows leading rows, in parallel."""
+    workers = _POOL._max_workers
+    if n_rows < 2 * min_rows or workers == 1:
+        fn(0, n_rows)
+        return
+    step = max(min_rows, -(-n_rows // (workers * 2)))
+    list(_POOL.map(lambda lo: fn(lo, min(lo + step, n_rows)), range(0, n_rows, step)))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -54,7 +71,15 @@ def coarse_tokens(feat_c: np.ndarray, pe: np.ndarray) -> np.ndarray:
 # --------------------------------------------------------------------------------------------------
 def _elu_feature_map(x: np.ndarray) -> np.ndarray:
     """elu(x) + 1  (linear_attention.py:10-11)."""
-    return (np.where(x > 0, x, np.expm1(np.minimum(x, 0))) + F32(1)).astype(F32)
+    out = np.empty(x.shape, F32)
+    x2, o2 = x.reshape(-1, x.shape[-1]), out.reshape(-1, x.shape[-1])
+
+    def body(lo, hi):
+        xb = x2[lo:hi]
+        o2[lo:hi] = np.where(xb > 0, xb, np.expm1(np.minimum(xb, 0))) + F32(1)
+
+    _blocked(body, x2.shape[0], 512)
+    return out
 
 
 def linear_attention(q, k, v, q_mask=None, kv_mask=None, eps=1e-6):
@@ -68,16 +93,28 @@ def linear_attention(q, k, v, q_mask=None, kv_mask=None, eps=1e-6):
         v = v * kv_mask[:, :, None, None].astype(F32)
     v_length = v.shape[1]
     v = v / F32(v_length)                                       # :41-42
-    KV = np.einsum("nshd,nshv->nhdv", K, v)                     # :43
-    Z = F32(1) / (np.einsum("nlhd,nhd->nlh", Q, K.sum(axis=1)) + F32(eps))  # :44
-    out = np.einsum("nlhd,nhdv,nlh->nlhv", Q, KV, Z) * F32(v_length)        # :45
-    return out.astype(F32)
+    Kt = K.transpose(0, 2, 3, 1)                                # [N,H,D,S]
+    KV = Kt @ v.transpose(0, 2, 1, 3)                           # einsum nshd,nshv->nhdv            :43
+    Qh = Q.transpose(0, 2, 1, 3)                                # [N,H,L,D]
+    Z = F32(1) / ((Qh @ K.sum(axis=1)[:, :, :, None])[..., 0] + F32(eps))   # einsum nlhd,nhd->nlh  :44
+    out = (Qh @ KV) * Z[..., None] * F32(v_length)              # einsum nlhd,nhdv,nlh->nlhv        :45
+    return np.ascontiguousarray(out.transpose(0, 2, 1, 3)).astype(F32)
 
 
 def layer_norm(x, g, b, eps=1e-5):
-    mu = x.mean(axis=-1, keepdims=True, dtype=np.float64)
-    var = ((x - mu) ** 2).mean(axis=-1, keepdims=True, dtype=np.float64)
-    return (((x - mu) / np.sqrt(var + eps)) * g + b).astype(F32)
+    """nn.LayerNorm over the last axis (biased variance), float32."""
+    out = np.empty(x.shape, F32)
+    x2, o2 = x.reshape(-1, x.shape[-1]), out.reshape(-1, x.shape[-1])
+
+    def body(lo, hi):
+        xb = x2[lo:hi]
+        mu = xb.mean(axis=-1, keepdims=True, dtype=F32)
+        d = xb - mu
+        var = (d * d).mean(axis=-1, keepdims=True, dtype=F32)
+        o2[lo:hi] = d / np.sqrt(var + F32(eps)) * g + b
+
+    _blocked(body, x2.shape[0], 512)
+    return out
 
 
 def encoder_layer(x, source, w, nhead, x_mask=None, source_mask=None):
@@ -122,8 +159,29 @@ def _logsumexp(x, axis):
 
 
 def _softmax(x, axis):
-    e = np.exp(x - x.max(axis=axis, keepdims=True))
-    return e / e.sum(axis=axis, keepdims=True)
+    """softmax along `axis` of a 2-D or 3-D float32 array (threaded over the other axes)."""
+    if x.ndim == 2:
+        return _softmax(x[None], axis + 1)[0]
+    out = np.empty(x.shape, F32)
+    if axis == 2:
+        x2, o2 = x.reshape(-1, x.shape[2]), out.reshape(-1, x.shape[2])
+
+        def body(lo, hi):
+            xb = x2[lo:hi]
+            e = np.exp(xb - xb.max(axis=1, keepdims=True))
+            o2[lo:hi] = e / e.sum(axis=1, keepdims=True)
+
+        _blocked(body, x2.shape[0])
+    elif axis == 1:
+        def body(lo, hi):  # column blocks
+            xb = x[:, :, lo:hi]
+            e = np.exp(xb - xb.max(axis=1, keepdims=True))
+            out[:, :, lo:hi] = e / e.sum(axis=1, keepdims=True)
+
+        _blocked(body, x.shape[2])
+    else:
+        raise ValueError(axis)
+    return out
 
 
 def log_optimal_transport(scores, alpha, iters):
@@ -184,13 +242,13 @@ def coarse_conf_matrix(feat_c0, feat_c1, cfg, mask_c0=None, mask_c1=None, bin_sc
     if mask_c0 is not None:
         pad = ~(mask_c0[..., None] & mask_c1[:, None])
     if cfg["match_type"] == "dual_softmax":
-        sim = np.einsum("nlc,nsc->nls", f0, f1) / F32(cfg["dsmax_temperature"])   # :109-110
+        sim = (f0 @ f1.transpose(0, 2, 1)) / F32(cfg["dsmax_temperature"])         # einsum nlc,nsc->nls  :109-110
         if pad is not None:
             sim[pad] = -INF                                                        # :111-114
         conf = _softmax(sim, 1) * _softmax(sim, 2)                                 # :115
         return conf.astype(F32), None
     if cfg["match_type"] == "sinkhorn":
-        sim = np.einsum("nlc,nsc->nls", f0, f1)                                    # :119
+        sim = f0 @ f1.transpose(0, 2, 1)                                           # einsum nlc,nsc->nls  :119
         if pad is not None:
             sim[pad] = -INF
         log_assign = log_optimal_transport(sim, bin_score, cfg["skh_iters"])      # :126-127
@@ -297,7 +355,7 @@ def fine_matching(f0, f1, mkpts0_c, mkpts1_c, b_ids, hw0_i, hw0_f, scale1=None):
     if m == 0:                                                                        # :33-41
         return {"expec_f": np.zeros((0, 3), F32), "mkpts0_f": mkpts0_c, "mkpts1_f": mkpts1_c}
     picked = f0[:, ww // 2, :]                                                        # :43
-    sim = np.einsum("mc,mrc->mr", picked, f1)                                         # :44
+    sim = (f1 @ picked[:, :, None])[..., 0]                                           # einsum mc,mrc->mr  :44
     heat = _softmax(F32(1.0 / c ** 0.5) * sim, 1)                                     # :45-46
     lin = np.linspace(-1, 1, W).astype(F32)
     gx = np.tile(lin[None, :], (W, 1)).reshape(-1)
