@@ -165,9 +165,6 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU port)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
     torch.backends.cudnn.allow_tf32 = False          # the backbone stays fp32 for parity (SURVEY.md §7 hard part 9)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = True
@@ -186,12 +183,14 @@ def run_b200(args):
     lib = _lib.load()
     stream = torch.cuda.current_stream()
 
-    def step(i0, i1):
+    t_start = time.perf_counter()
+
+    def note(msg):
+        print(f"[bench rank {rank} +{time.perf_counter() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+    def local_step(i0, i1):
         data = {"image0": i0, "image1": i1}
         model(data)
-        if world > 1:
-            lo, _ = parallel.shard_range(B * world, rank, world)
-            parallel.all_gather_matches(data, lo, cap)
         return data
 
     def timed(fn, n):
@@ -207,6 +206,42 @@ def run_b200(args):
         torch.cuda.synchronize()
         return sum(a.elapsed_time(b) for a, b in evs)
 
+    # Phase A -- everything that loads CUDA kernels runs BEFORE the NCCL communicator exists.  With the
+    # communicator created first, the first launch of every not-yet-loaded kernel module stalls for tens of
+    # seconds on this image (measured with tools/mgpu_diag.py: first cuDNN convolution 54 s after an eager
+    # `init_process_group`, 0.5 s before it) -- slow module loading, not a deadlock.
+    K, Wm = max(1, args.steps), max(3, args.warmup)
+    lo_pair, _ = parallel.shard_range(B * world, rank, world)
+    last = None
+    for _ in range(Wm):
+        last = local_step(d_img0, d_img1)
+        parallel.unpack_matches(parallel.pack_matches(last, lo_pair, cap).unsqueeze(0))
+    m_per_step = int(last["mconf"].shape[0])
+    out_host = {}
+
+    def e2e_local():
+        i0 = h_img0.to(dev, non_blocking=True)
+        i1 = h_img1.to(dev, non_blocking=True)
+        d = local_step(i0, i1)
+        if world > 1 and dist.is_initialized():
+            d = parallel.all_gather_matches(d, lo_pair, cap)
+        for k in ("mkpts0_f", "mkpts1_f", "mconf", "m_bids"):
+            out_host[k] = d[k].cpu()
+
+    timed(e2e_local, 1)
+    torch.tensor([1.0], dtype=torch.float64, device=dev).max().item()
+    note("single-process warm-up done")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        note("process group up")
+
+    def step(i0, i1):
+        data = local_step(i0, i1)
+        if world > 1:
+            parallel.all_gather_matches(data, lo_pair, cap)
+        return data
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -219,11 +254,11 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    K, Wm = max(1, args.steps), max(3, args.warmup)
-    last = None
-    for _ in range(Wm):
-        last = step(d_img0, d_img1)
-    m_per_step = int(last["mconf"].shape[0])
+    for _ in range(2 if world > 1 else 0):   # collective warm-up (NCCL channels, all-gather kernel)
+        step(d_img0, d_img1)
+    max_over_ranks(0.0)
+    barrier()
+    note("collective warm-up done")
 
     # ---- device-resident throughput
     barrier()
@@ -235,21 +270,13 @@ def run_b200(args):
     ms_step = max_over_ranks(ms_total / K)
     value = B * world / (ms_step * 1e-3)
 
+    note(f"device-resident timing done: {ms_step:.2f} ms/step")
     # ---- end to end through the public API: pinned host images in, host match lists out
-    out_host = {}
-
-    def e2e_step():
-        i0 = h_img0.to(dev, non_blocking=True)
-        i1 = h_img1.to(dev, non_blocking=True)
-        d = step(i0, i1)
-        for k in ("mkpts0_f", "mkpts1_f", "mconf", "m_bids"):
-            out_host[k] = d[k].cpu()
-
     for _ in range(2):
-        e2e_step()
+        e2e_local()
     barrier()
     t0 = time.perf_counter()
-    ms_e2e_dev = timed(e2e_step, K)
+    ms_e2e_dev = timed(e2e_local, K)
     barrier()
     wall_e2e = (time.perf_counter() - t0) * 1e3
     ms_e2e = max_over_ranks(ms_e2e_dev / K)
@@ -257,6 +284,7 @@ def run_b200(args):
     d2h = sum(v.numel() * v.element_size() for v in out_host.values())
     e2e = {"value": B * world / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "wall_ms_per_step_incl_l2_flush": wall_e2e / K}
+    note("e2e timing done")
 
     # ---- per-kernel CUDA-event timing of the tensor-core kernels (rank 0), separate pass
     roof, kernels = None, {}
@@ -265,7 +293,7 @@ def run_b200(args):
         nprof = 3
         for _ in range(nprof):
             flush.zero_()
-            step(d_img0, d_img1)
+            local_step(d_img0, d_img1)   # rank-local: the other ranks are already waiting at the final barrier
         torch.cuda.synchronize()
         rec = _lib.timing_collect()
         _lib.timing_enable(False)

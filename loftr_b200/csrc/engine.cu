@@ -63,35 +63,45 @@ static bool g_timing = false;
 static std::vector<TimingRec> g_recs;
 static std::mutex g_timing_mu;
 
+// The library carries its own (static) CUDA runtime, whose notion of "current device" is independent of the
+// caller's (e.g. torch's).  Every entry point therefore binds the calling thread to the device that owns the
+// buffers it was given -- otherwise a process working on cuda:1 would launch on device 0 through the legacy
+// default stream.
+constexpr int kMaxDevices = 64;
+static int bind_device_of(const void* dev_ptr) {
+  if (!dev_ptr) return fail("null device pointer");
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, dev_ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail("no usable CUDA device for this buffer (%s); loftr_b200 has no CPU fallback", cudaGetErrorString(e));
+  }
+  if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)
+    return fail("expected a CUDA device pointer; loftr_b200 has no CPU fallback");
+  int cur = -1;
+  LB_CUDA(cudaGetDevice(&cur));
+  if (cur != attr.device) LB_CUDA(cudaSetDevice(attr.device));
+  return 0;
+}
+
 static int device_check(int* sm_count) {
-  static std::once_flag once;
-  static int sms = 0, status = 0;
-  static char msg[256] = "";
-  std::call_once(once, [&]() {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) {
-      status = 1;
-      snprintf(msg, sizeof(msg), "no CUDA device: %s", cudaGetErrorString(e));
-      return;
-    }
+  static std::mutex mu;
+  static int sms[kMaxDevices] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail("no CUDA device: %s", cudaGetErrorString(e));
+  if (dev < 0 || dev >= kMaxDevices) return fail("device index %d out of range", dev);
+  std::lock_guard<std::mutex> lk(mu);
+  if (sms[dev] == 0) {
     cudaDeviceProp prop;
     e = cudaGetDeviceProperties(&prop, dev);
-    if (e != cudaSuccess) {
-      status = 1;
-      snprintf(msg, sizeof(msg), "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
-      return;
-    }
-    if (prop.major != 10) {
-      status = 1;
-      snprintf(msg, sizeof(msg), "loftr_b200 requires an sm_100 (B200) device, found sm_%d%d; there is no fallback",
-               prop.major, prop.minor);
-      return;
-    }
-    sms = prop.multiProcessorCount;
-  });
-  if (status) return fail("%s", msg);
-  *sm_count = sms;
+    if (e != cudaSuccess) return fail("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+      return fail("loftr_b200 requires an sm_100 (B200) device, found sm_%d%d; there is no fallback", prop.major,
+                  prop.minor);
+    sms[dev] = prop.multiProcessorCount;
+  }
+  *sm_count = sms[dev];
   return 0;
 }
 
@@ -167,10 +177,12 @@ static int launch_gemm(int tag, const Planes& A, const Planes& B, int batches, i
   constexpr int smem_bytes = S::kRingBytes + S::kBarBytes + Epi::kSmemBytes + 1024;
   static_assert(smem_bytes <= 232448, "shared memory budget exceeded");
   auto kern = gemm_split_kernel<BN, Epi>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  static bool configured[kMaxDevices] = {false};  // per instantiation and device
+  int dev = 0;
+  LB_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev]) {
     LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured = true;
+    configured[dev] = true;
   }
   const long items = static_cast<long>(batches) * s.m_tiles * s.n_chunks;
   const int grid = static_cast<int>(items < sms ? items : sms);
@@ -385,9 +397,10 @@ int lb_timing_collect(double* total_ms, long long* counts, int n) {
 
 int lb_split_planes(const float* x, long rows, int cols, int ld_x, void* hi, void* lo, int ld_pl, int col0,
                     void* stream) {
-  int sms;
-  LB_TRY(device_check(&sms));
   if (rows <= 0 || cols <= 0) return 0;
+  int sms;
+  LB_TRY(bind_device_of(x));
+  LB_TRY(device_check(&sms));
   const long total = rows * cols;
   const int grid = static_cast<int>(total / 256 + 1 < 4096 ? total / 256 + 1 : 4096);
   split_planes_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -400,6 +413,7 @@ int lb_gemm_split(const void* a_hi, const void* a_lo, long lda, long a_batch_str
                   const void* b_lo, long ldb, long b_batch_stride, float* out, long ldo, long o_batch_stride,
                   int batches, int M, int N, int K, void* stream) {
   if (N % 32 != 0) return fail("lb_gemm_split: N must be a multiple of 32");
+  LB_TRY(bind_device_of(out));
   if (batches > 1 && o_batch_stride != static_cast<long>(M) * ldo)
     return fail("lb_gemm_split: output batches must be densely stacked (o_batch_stride == M*ldo)");
   Planes A{a_hi, a_lo, lda, batches > 1 ? a_batch_stride : 0};
@@ -418,6 +432,8 @@ int lb_gemm_split(const void* a_hi, const void* a_lo, long lda, long a_batch_str
 int lb_coarse_prep(const float* feat_nchw, const float* pe, int n_img, int C, int h, int w, int pe_h, int pe_w,
                    float* x_f32, void* cat_hi, void* cat_lo, void* stream) {
   int sms;
+  if (n_img <= 0) return 0;
+  LB_TRY(bind_device_of(x_f32));
   LB_TRY(device_check(&sms));
   if (h > pe_h || w > pe_w) return fail("feature map %dx%d exceeds the position-encoding table %dx%d", h, w, pe_h, pe_w);
   if (n_img <= 0) return 0;
@@ -439,6 +455,8 @@ size_t lb_transformer_workspace_bytes(int d_model, int nhead, int n_groups, int 
 int lb_transformer_forward(const LbEncoderLayerWeights* layers, const int* kinds, int n_layers, int d_model,
                            int nhead, const LbTransformerState* st, void* ws, size_t ws_bytes, void* stream) {
   int sms;
+  if (st->n_groups <= 0) return 0;
+  LB_TRY(bind_device_of(st->x_f32));
   LB_TRY(device_check(&sms));
   const int C = d_model, H = nhead;
   const bool coarse = (C == 256 && H == 8);
@@ -532,6 +550,7 @@ size_t lb_coarse_match_workspace_bytes(int n_pairs, int L, int S) {
 
 int lb_coarse_match(const LbCoarseMatchArgs* a, void* ws, size_t ws_bytes, void* stream) {
   int sms;
+  LB_TRY(bind_device_of(a->count));
   LB_TRY(device_check(&sms));
   const int n = a->n_pairs, L = a->L, S = a->S, C = a->C;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -713,8 +732,9 @@ size_t lb_fine_preprocess_workspace_bytes(long M, int W, int Cf) {
 
 int lb_fine_preprocess(const LbFinePreprocessArgs* a, void* ws, size_t ws_bytes, void* stream) {
   int sms;
-  LB_TRY(device_check(&sms));
   if (a->M <= 0) return 0;
+  LB_TRY(bind_device_of(a->x_f32));
+  LB_TRY(device_check(&sms));
   if (a->Cf != 128 || a->Cc > 256) return fail("fine preprocess built for Cf=128, Cc<=256 (got %d, %d)", a->Cf, a->Cc);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int WW = a->W * a->W;
@@ -758,8 +778,9 @@ int lb_fine_preprocess(const LbFinePreprocessArgs* a, void* ws, size_t ws_bytes,
 
 int lb_fine_match(const LbFineMatchArgs* a, void* stream) {
   int sms;
-  LB_TRY(device_check(&sms));
   if (a->M <= 0) return 0;
+  LB_TRY(bind_device_of(a->expec_f));
+  LB_TRY(device_check(&sms));
   if (a->W * a->W > 32) return fail("fine window %dx%d exceeds one warp", a->W, a->W);
   FineMatchParams p;
   p.f0 = a->f0; p.f1 = a->f1; p.W = a->W; p.C = a->C; p.M = a->M;

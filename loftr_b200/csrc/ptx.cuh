@@ -60,14 +60,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-// Bounded wait: a protocol bug must become a trap (reported as a launch failure), never a hung GPU.
-#ifndef LB_MBAR_SPIN_LIMIT
-#define LB_MBAR_SPIN_LIMIT (1u << 24)
+// Bounded wait: a protocol bug must become a trap (reported as a launch failure) within seconds, never a
+// hung GPU.  No legitimate wait in these kernels lasts longer than a few milliseconds.
+#ifndef LB_MBAR_TIMEOUT_CYCLES
+#define LB_MBAR_TIMEOUT_CYCLES (6000000000ll)  // ~3 s at 1.9 GHz
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > LB_MBAR_SPIN_LIMIT) {
+    if (clock64() - t0 > LB_MBAR_TIMEOUT_CYCLES) {
       asm volatile("trap;");
     }
   }

@@ -48,7 +48,8 @@ def unpack_matches(gathered: torch.Tensor) -> dict:
 
 def all_gather_matches(data: dict, pair_offset: int, capacity: int, group=None) -> dict:
     """Every rank ends with the global match list (ranks hold contiguous pair blocks, so concatenating in
-    rank order preserves the reference's ascending (b, i) ordering)."""
+    rank order preserves the reference's ascending (b, i) ordering).  `capacity` MUST be the same on every rank
+    (static-shape collective): use max_pairs_per_rank * min(L, S)."""
     buf = pack_matches(data, pair_offset, capacity)
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return unpack_matches(buf.unsqueeze(0))
