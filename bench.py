@@ -64,8 +64,15 @@ def cpu_pairs_per_sec(thr, steps, warmup, pairs_per_step=1):
     import torch
     import loftr_b200
     from oracle import loftr_oracle as O
-    cores = os.cpu_count() or 1
+    # all host cores up to 32 threads: beyond that the ~1-10 ms numpy / BLAS calls of this workload only
+    # oversubscribe (measured on the 128-core GPU host: 12.1 s/pair with 128 threads)
+    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
     torch.manual_seed(0)
     cfg = loftr_b200.get_cfg("indoor_ds", thr=thr)
     model = loftr_b200.LoFTR(cfg).eval()

@@ -25,7 +25,7 @@ INF = 1e9  # coarse_matching.py:6
 # numpy ufuncs release the GIL, so the big elementwise passes (softmax over L x S, LayerNorm, elu) are
 # row-blocked over a thread pool -- the reference's torch-CPU kernels use every host core too, and this
 # port is also the timed CPU baseline (bench.py).  Dense products go through BLAS (`@`).
-_POOL = ThreadPoolExecutor(max_workers=os.cpu_count() or 1)
+_POOL = ThreadPoolExecutor(max_workers=min(os.cpu_count() or 1, int(os.environ.get("LOFTR_ORACLE_THREADS", "32"))))
 
 
 def _blocked(fn, n_rows, min_rows=64):

@@ -11,6 +11,9 @@ groups=(
   "tests/test_engine_gpu.py::test_fine_level_matches_oracle"
   "tests/test_engine_gpu.py::test_end_to_end_matches_reference_golden"
   "tests/test_engine_gpu.py::test_end_to_end_640x480_vs_oracle"
+  "tests/test_engine_gpu.py::test_outdoor_832_masked_vs_oracle"
+  "tests/test_engine_gpu.py::test_sinkhorn_640x480_vs_oracle"
+  "tests/test_engine_gpu.py::test_resolution_sweep_properties"
   "tests/test_engine_gpu.py::test_no_cpu_fallback"
 )
 rc=0

@@ -214,3 +214,83 @@ def test_no_cpu_fallback():
     model = loftr_b200.LoFTR(loftr_b200.get_cfg("indoor_ds")).eval()
     with pytest.raises(RuntimeError):
         model({"image0": torch.rand(1, 1, 64, 64), "image1": torch.rand(1, 1, 64, 64)})
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE.json configs
+def test_outdoor_832_masked_vs_oracle():
+    """configs[2] shape: 832x832 (L = S = 10816), MegaDepth-style padding masks + scales, one pair."""
+    case = {"name": "outdoor", "n": 1, "hw0": (832, 832), "hw1": (832, 832), "thr": 0.0, "images": "smooth",
+            "valid0": [(832, 624)], "valid1": [(640, 832)], "scales": True}
+    model, data = _run_engine(case)
+    out = util.oracle_forward(case, backbone_device=DEV)
+    got = {k: data[k].cpu().numpy() for k in ["b_ids", "i_ids", "j_ids", "mconf", "mkpts0_c", "mkpts1_c", "mkpts0_f",
+                                              "mkpts1_f"]}
+    assert len(out["b_ids"]) > 500
+    stats = util.compare_matches(got, out, None, conf_rtol=1e-3, px_tol=0.5, min_overlap=0.99, label="832 masked")
+    # nothing may come from the padded area or its border
+    i, j = got["i_ids"], got["j_ids"]
+    assert (i % 104 < 624 // 8 - 2).all() and (j // 104 < 640 // 8 - 2).all()
+    print("832x832 masked parity:", stats)
+
+
+def test_sinkhorn_640x480_vs_oracle():
+    """configs[4] shape: indoor_ot at 640x480 (one pair)."""
+    case = {"name": "ot_full", "n": 1, "hw0": (480, 640), "hw1": (480, 640), "thr": 0.0, "images": "smooth",
+            "match_type": "sinkhorn"}
+    model, data = _run_engine(case)
+    out = util.oracle_forward(case, backbone_device=DEV)
+    got = {k: data[k].cpu().numpy() for k in ["b_ids", "i_ids", "j_ids", "mconf", "mkpts0_c", "mkpts1_c", "mkpts0_f",
+                                              "mkpts1_f"]}
+    assert len(out["b_ids"]) > 300
+    stats = util.compare_matches(got, out, None, conf_rtol=1e-3, px_tol=0.5, min_overlap=0.99, label="ot 640x480")
+    print("sinkhorn 640x480 parity:", stats)
+
+
+@pytest.mark.parametrize("hw", [(240, 320), (960, 1280)])
+def test_resolution_sweep_properties(hw):
+    """configs[3]: token-count scaling.  320x240 is checked against the oracle; at 1280x960 (L = 19200, where the
+    oracle's L x S matrices no longer fit comfortably) size-independent properties are checked instead:
+    duplicate pairs in a batch give identical lists, and every reported match is a mutual nearest neighbour
+    with the reported confidence when its row / column are recomputed in fp64."""
+    h, w = hw
+    case = {"name": "sweep", "n": 1, "hw0": hw, "hw1": hw, "thr": 0.0, "images": "smooth"}
+    if h * w <= 320 * 240:
+        model, data = _run_engine(case)
+        out = util.oracle_forward(case, backbone_device=DEV)
+        got = {k: data[k].cpu().numpy() for k in ["b_ids", "i_ids", "j_ids", "mconf", "mkpts0_c", "mkpts1_c",
+                                                  "mkpts0_f", "mkpts1_f"]}
+        util.compare_matches(got, out, None, conf_rtol=1e-3, px_tol=0.5, min_overlap=0.99, label=str(hw))
+        return
+    model, cfg, _ = util.build_model(case, DEV)
+    inp = build_inputs(case)
+    i0, i1 = _t(inp["image0"]), _t(inp["image1"])
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    one = {"image0": i0, "image1": i1}
+    model(one)
+    two = {"image0": torch.cat([i0, i0]), "image1": torch.cat([i1, i1])}
+    model(two)
+    m = one["mconf"].shape[0]
+    assert m > 1000
+    nb = (two["m_bids"] == 0).sum().item()
+    assert two["mconf"].shape[0] == 2 * nb
+    for k in ("i_ids", "j_ids"):
+        assert torch.equal(two[k][:nb], two[k][nb:])            # the two copies inside one batch agree exactly
+    assert torch.equal(two["mconf"][:nb], two["mconf"][nb:])
+    # fp64 re-evaluation of sampled matches from the engine's own coarse features
+    f0, f1 = one["_feat_c0"][0].double() / 16.0, one["_feat_c1"][0].double() / 16.0   # / sqrt(256)
+    idx = torch.linspace(0, m - 1, 64, device=DEV).long()
+    ii, jj = one["i_ids"][idx], one["j_ids"][idx]
+    sim_rows = (f0[ii] @ f1.T) / 0.1                              # [64, S]
+    sim_cols = (f0 @ f1[jj].T) / 0.1                              # [L, 64]
+    row_lse = torch.logsumexp(sim_rows, 1)                        # rowLSE_i
+    col_lse = torch.logsumexp(sim_cols, 0)                        # colLSE_j
+    s_ij = sim_rows[torch.arange(64), jj]
+    conf = torch.exp(2 * s_ij - row_lse - col_lse)
+    rel = ((one["mconf"][idx].double() - conf).abs() / conf).max().item()
+    assert rel < 1e-3, f"mconf differs from the fp64 re-evaluation by {rel:.2e}"
+    # mutual nearest neighbour: j maximises 2 s_ij - colLSE_j over the row needs all colLSE; check the weaker,
+    # size-independent necessary condition on the column side: i maximises s_ij - rowLSE_i ... via rows' own LSE
+    full_row_lse = torch.cat([torch.logsumexp((f0[a:a + 2048] @ f1.T) / 0.1, 1) for a in range(0, f0.shape[0], 2048)])
+    col_key = 2 * sim_cols - full_row_lse[:, None]
+    assert torch.equal(col_key.argmax(0), ii), "a reported match is not the column's nearest neighbour"
