@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--thr", type=float, default=0.0)
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--backbone", default="b200", choices=["b200", "torch"],
+                    help="b200: implicit-GEMM convolutions on tcgen05 (default); torch: PyTorch/cuDNN fp32 backbone")
     return ap.parse_args()
 
 
@@ -179,7 +181,7 @@ def run_b200(args):
     B = args.batch
     torch.manual_seed(0)
     cfg = loftr_b200.get_cfg("indoor_ds", thr=args.thr)
-    model = loftr_b200.LoFTR(cfg).eval().to(dev)
+    model = loftr_b200.LoFTR(cfg, backbone_impl=args.backbone).eval().to(dev)
     g = torch.Generator().manual_seed(1000 + rank)
     h_img0 = torch.rand(B, 1, H, W_IMG, generator=g).pin_memory()
     h_img1 = torch.rand(B, 1, H, W_IMG, generator=g).pin_memory()
@@ -326,6 +328,16 @@ def run_b200(args):
                     "issued_flops_factor": 3, "note": "three fp16 MMAs per product (hi*hi+hi*lo+lo*hi) for fp32-level accuracy; "
                     "frac counts algorithmic flops once"}
 
+        if "backbone_conv" in kernels:
+            from torch.utils.flop_counter import FlopCounterMode
+            with FlopCounterMode(display=False) as fcm:
+                model.backbone(torch.cat([d_img0, d_img1]))
+            conv_flops = float(fcm.get_total_flops())
+            tot_ms = kernels["backbone_conv"]["avg_ms"] * kernels["backbone_conv"]["launches_per_step"]
+            ach = conv_flops / (tot_ms * 1e-3) * 1e-12
+            kernels["backbone_conv"].update({"algorithmic_flops_per_step": conv_flops, "total_ms_per_step": tot_ms,
+                                             "achieved_tflops": ach, "frac_of_measured_bf16_sustained": ach / pk["bf16_tflops_sustained"]})
+
     # ---- CPU baseline (rank 0, single GPU run only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -343,6 +355,8 @@ def run_b200(args):
             "config": {"workload": f"batch={B} 640x480 pairs per GPU, indoor_ds dual-softmax, thr={args.thr}",
                        "global_batch": B * world, "thr": args.thr, "weights": "random-init seed 0",
                        "matches_per_step_rank0": m_per_step, "l2": "256 MiB flush buffer written before every timed step",
+                       "backbone": ("ResNetFPN_8_2 as implicit-GEMM convolutions on tcgen05 (3x fp16 split, fp32 accumulate)"
+                                    if args.backbone == "b200" else "PyTorch/cuDNN fp32 (TF32 off)"),
                        "parallelism": f"pairs sharded over {world} GPU(s), one NCCL all-gather of match lists"},
             "clocks": clk.summary(),
             "e2e": e2e, "gpu_launches": int(launches),

@@ -63,11 +63,48 @@ int lb_gemm_split(const void* a_hi, const void* a_lo, long lda, long a_batch_str
                   const void* b_lo, long ldb, long b_batch_stride, float* out, long ldo, long o_batch_stride,
                   int batches, int M, int N, int K, void* stream);
 
-/* feat [n_img, C, h, w] fp32 NCHW + pe [C, pe_h, pe_w] -> x_f32 [n_img*h*w, C], cat planes [rows, 2C] cols [0,C). */
-int lb_coarse_prep(const float* feat_nchw, const float* pe, int n_img, int C, int h, int w, int pe_h, int pe_w,
+/* feat fp32 (NCHW [n_img, C, h, w], or NHWC [n_img, h, w, C] when nhwc != 0) + pe [C, pe_h, pe_w]
+ * -> x_f32 [n_img*h*w, C], cat planes [rows, 2C] cols [0,C). */
+int lb_coarse_prep(const float* feat, int nhwc, const float* pe, int n_img, int C, int h, int w, int pe_h, int pe_w,
                    float* x_f32, void* cat_hi, void* cat_lo, void* stream);
 
-/* Weights of one LoFTREncoderLayer (state_dict names in comments), as fp16 planes of the [out, in] matrices. */
+/* ResNetFPN_8_2 local-feature CNN on tensor cores (reference src/loftr/backbone/resnet_fpn.py:43-118; SURVEY.md
+ * §8(f) rank 1).  One LbConvWeights per Conv2d(+BatchNorm2d in eval mode, folded to scale/shift; scale = 1,
+ * shift = 0 for a bare convolution).  Weight planes: [cout, k*k * ceil(cin/64)*64] = for every tap the cin
+ * channels zero-padded to a multiple of 64 (tap-major), fp16 hi/lo. */
+typedef struct LbConvWeights {
+  const void* w_hi;
+  const void* w_lo;
+  const float* scale;  /* [cout] */
+  const float* shift;  /* [cout] */
+  int cin, cout, ksize, stride;
+} LbConvWeights;
+
+typedef struct LbBackboneWeights {
+  const float* stem_wt;    /* conv1.weight [cout,1,7,7] stored transposed as [49, cout] fp32 */
+  const float* stem_scale; /* bn1 folded */
+  const float* stem_shift;
+  int stem_cout;
+  LbConvWeights l1[4];     /* layer1.{0,1}.{conv1,conv2} (+bn1/bn2) */
+  LbConvWeights l2[4];     /* layer2.{0,1}.{conv1,conv2}; l2[0] has stride 2 */
+  LbConvWeights l2_down;   /* layer2.0.downsample.{0,1} */
+  LbConvWeights l3[4];
+  LbConvWeights l3_down;
+  LbConvWeights l3_out;    /* layer3_outconv */
+  LbConvWeights l2_out;    /* layer2_outconv */
+  LbConvWeights l2_out2[2];/* layer2_outconv2.{0(+1 BN, LeakyReLU), 3} */
+  LbConvWeights l1_out;    /* layer1_outconv */
+  LbConvWeights l1_out2[2];/* layer1_outconv2.{0(+1), 3} */
+} LbBackboneWeights;
+
+size_t lb_backbone_workspace_bytes(const LbBackboneWeights* w /*host*/, int N, int H, int W);
+/* images [N,1,H,W] fp32 -> feat_c NHWC fp32 [N,H/8,W/8,block_dims[2]], feat_f NHWC fp32 [N,H/2,W/2,block_dims[0]] */
+int lb_backbone_forward(const LbBackboneWeights* w /*host*/, const float* images, int N, int H, int W,
+                        float* feat_c_nhwc, float* feat_f_nhwc, void* ws, size_t ws_bytes, void* stream);
+
+/* Weights of one LoFTREncoderLayer (state_dict names in comments), as fp16 planes of the [out, in] matrices.
+ * Each weight matrix may be pre-scaled by a power of two 2^e before it is split (keeps the fp16 `lo` plane out of
+ * the subnormal range); s_* = 2^-e is applied to the fp32 accumulator (exact). */
 typedef struct LbEncoderLayerWeights {
   const void* wqkv_hi; /* [3C, C]: rows = q_proj.weight, k_proj.weight, v_proj.weight */
   const void* wqkv_lo;
@@ -81,6 +118,7 @@ typedef struct LbEncoderLayerWeights {
   const float* ln1_b;
   const float* ln2_g;
   const float* ln2_b;
+  float s_qkv, s_m, s_1, s_2;
 } LbEncoderLayerWeights;
 
 /* Token state of a LocalFeatureTransformer run over two token sets (feat0 rows first, then feat1 rows). */
@@ -152,8 +190,9 @@ typedef struct LbFinePreprocessArgs {
   const float* down_b;
   const float* merge_w2t; /* fine_preprocess.merge_feat.weight[:, Cf:2Cf] TRANSPOSED [Cf, Cf] (fp32) */
   const float* merge_b;   /* fine_preprocess.merge_feat.bias [Cf] */
-  const void* merge_w_hi; /* planes of merge_w[:, 0:Cf]  -> [Cf, Cf] */
+  const void* merge_w_hi; /* planes of merge_w[:, 0:Cf] * 2^e  -> [Cf, Cf] */
   const void* merge_w_lo;
+  float merge_acc_scale;  /* 2^-e */
   /* outputs: fine transformer state, rows = side*M*W*W + m*W*W + k */
   float* x_f32;           /* [2*M*W*W, Cf] */
   void* cat_hi;           /* [2*M*W*W, 2Cf] */

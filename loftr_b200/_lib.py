@@ -27,7 +27,20 @@ c_size_t = C.c_size_t
 class LbEncoderLayerWeights(C.Structure):
     _fields_ = [(n, c_void_p) for n in (
         "wqkv_hi", "wqkv_lo", "wm_hi", "wm_lo", "w1_hi", "w1_lo", "w2_hi", "w2_lo",
-        "ln1_g", "ln1_b", "ln2_g", "ln2_b")]
+        "ln1_g", "ln1_b", "ln2_g", "ln2_b")] + [(n, c_float) for n in ("s_qkv", "s_m", "s_1", "s_2")]
+
+
+class LbConvWeights(C.Structure):
+    _fields_ = [("w_hi", c_void_p), ("w_lo", c_void_p), ("scale", c_void_p), ("shift", c_void_p),
+                ("cin", c_int), ("cout", c_int), ("ksize", c_int), ("stride", c_int)]
+
+
+class LbBackboneWeights(C.Structure):
+    _fields_ = [("stem_wt", c_void_p), ("stem_scale", c_void_p), ("stem_shift", c_void_p), ("stem_cout", c_int),
+                ("l1", LbConvWeights * 4), ("l2", LbConvWeights * 4), ("l2_down", LbConvWeights),
+                ("l3", LbConvWeights * 4), ("l3_down", LbConvWeights), ("l3_out", LbConvWeights),
+                ("l2_out", LbConvWeights), ("l2_out2", LbConvWeights * 2), ("l1_out", LbConvWeights),
+                ("l1_out2", LbConvWeights * 2)]
 
 
 class LbTransformerState(C.Structure):
@@ -60,7 +73,7 @@ class LbFinePreprocessArgs(C.Structure):
         ("feat_c", c_void_p), ("n_pairs", c_int), ("L", c_int), ("S", c_int), ("M", c_long),
         ("b_ids", c_void_p), ("i_ids", c_void_p), ("j_ids", c_void_p),
         ("down_wt", c_void_p), ("down_b", c_void_p), ("merge_w2t", c_void_p), ("merge_b", c_void_p),
-        ("merge_w_hi", c_void_p), ("merge_w_lo", c_void_p),
+        ("merge_w_hi", c_void_p), ("merge_w_lo", c_void_p), ("merge_acc_scale", c_float),
         ("x_f32", c_void_p), ("cat_hi", c_void_p), ("cat_lo", c_void_p),
     ]
 
@@ -85,8 +98,11 @@ SIGNATURES = {
     "lb_split_planes": (c_int, [c_void_p, c_long, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "lb_gemm_split": (c_int, [c_void_p, c_void_p, c_long, c_long, c_void_p, c_void_p, c_long, c_long, c_void_p,
                               c_long, c_long, c_int, c_int, c_int, c_int, c_void_p]),
-    "lb_coarse_prep": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
-                               c_void_p, c_void_p]),
+    "lb_coarse_prep": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                               c_void_p, c_void_p, c_void_p]),
+    "lb_backbone_workspace_bytes": (c_size_t, [C.POINTER(LbBackboneWeights), c_int, c_int, c_int]),
+    "lb_backbone_forward": (c_int, [C.POINTER(LbBackboneWeights), c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_size_t, c_void_p]),
     "lb_transformer_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "lb_transformer_forward": (c_int, [C.POINTER(LbEncoderLayerWeights), C.POINTER(c_int), c_int, c_int, c_int,
                                        C.POINTER(LbTransformerState), c_void_p, c_size_t, c_void_p]),

@@ -52,9 +52,9 @@ static int fail(const char* fmt, ...) {
 // Optional per-launch CUDA-event timing of the tensor-core kernels (bench.py's roofline leg): events are
 // recorded on the launching stream right around the kernel, and only while timing is enabled.
 enum Tag { TAG_GEMM_TEST = 0, TAG_PROJ, TAG_MERGE_LN, TAG_MLP1, TAG_MLP2_LN, TAG_SCORE_LSE, TAG_SCORE_ARGMAX,
-           TAG_FINE_MERGE, TAG_COUNT };
+           TAG_FINE_MERGE, TAG_CONV, TAG_COUNT };
 static const char* kTagNames[TAG_COUNT] = {"gemm_test", "proj_act", "merge_ln", "mlp1_relu", "mlp2_ln_res",
-                                           "score_lse", "score_argmax", "fine_merge"};
+                                           "score_lse", "score_argmax", "fine_merge", "backbone_conv"};
 struct TimingRec {
   cudaEvent_t e0, e1;
   int tag;
@@ -139,6 +139,27 @@ static int make_map(CUtensorMap* m, const void* base, long K, long rows, long ba
   return 0;
 }
 
+// NHWC fp16 plane viewed as [N][H][W][C] (row stride ld elements); box = 64 channels x (16*stride) x (8*stride)
+// x 1 with element strides (1, stride, stride, 1): an 8 x 16 patch of (strided) pixels per load.
+static int make_map_nhwc(CUtensorMap* m, const void* base, int C, int W, int H, int N, long ld, int stride) {
+  auto enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail("plane pointer not 16-byte aligned");
+  if ((ld * 2) % 16 != 0) return fail("NHWC channel stride must be a multiple of 8 elements (got %ld)", ld);
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(ld * 2), static_cast<cuuint64_t>(ld * 2 * W),
+                           static_cast<cuuint64_t>(ld * 2 * W) * H};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(kConvTileW * stride),
+                       static_cast<cuuint32_t>(kConvTileH * stride), 1};
+  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (NHWC) failed with CUresult %d", static_cast<int>(r));
+  return 0;
+}
+
 struct Planes {
   const void* hi;
   const void* lo;
@@ -165,6 +186,7 @@ static int launch_gemm(int tag, const Planes& A, const Planes& B, int batches, i
   if (n_chunks <= 0 || n_chunks > s.n_tiles) n_chunks = s.n_tiles;
   s.tiles_per_chunk = (s.n_tiles + n_chunks - 1) / n_chunks;
   s.n_chunks = (s.n_tiles + s.tiles_per_chunk - 1) / s.tiles_per_chunk;
+  s.conv = ConvGeom{0, 0, 0, 0, 0, 0};
 
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   LB_TRY(make_map(&ma_hi, A.hi, K, M, batches, A.ld, A.batch_stride, kBlockM));
@@ -187,6 +209,69 @@ static int launch_gemm(int tag, const Planes& A, const Planes& B, int batches, i
   const long items = static_cast<long>(batches) * s.m_tiles * s.n_chunks;
   const int grid = static_cast<int>(items < sms ? items : sms);
   TimingRec rec{nullptr, nullptr, tag};
+  if (g_timing) {
+    LB_CUDA(cudaEventCreate(&rec.e0));
+    LB_CUDA(cudaEventCreate(&rec.e1));
+    LB_CUDA(cudaEventRecord(rec.e0, st));
+  }
+  kern<<<grid, kGemmThreads, smem_bytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, s, ep);
+  LB_LAUNCHED();
+  if (g_timing) {
+    LB_CUDA(cudaEventRecord(rec.e1, st));
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    g_recs.push_back(rec);
+  }
+  return 0;
+}
+
+// Implicit-GEMM convolution launch: in = NHWC planes [N, H_in, W_in, ld_in] with Cin valid channels; weights =
+// planes [Cout, taps * cin_blocks * 64] (zero padded per tap); out pixel grid H_out x W_out.
+struct ConvDesc {
+  int N, H_in, W_in, Cin, H_out, W_out, Cout, ksize, stride, pad;
+};
+template <int BN>
+static int launch_conv(const Planes& in, const Planes& wgt, const ConvDesc& d, const typename EpiConv<BN>::Params& ep_in,
+                       cudaStream_t st) {
+  using Epi = EpiConv<BN>;
+  int sms = 0;
+  LB_TRY(device_check(&sms));
+  GemmShape s;
+  const int cin_blocks = (d.Cin + kBlockK - 1) / kBlockK;
+  const int tiles_h = (d.H_out + kConvTileH - 1) / kConvTileH;
+  const int tiles_w = (d.W_out + kConvTileW - 1) / kConvTileW;
+  s.batches = d.N;
+  s.M = tiles_h * tiles_w * kBlockM;
+  s.N = d.Cout;
+  s.K = d.ksize * d.ksize * cin_blocks * kBlockK;
+  s.b_batched = 0;
+  s.m_tiles = tiles_h * tiles_w;
+  s.n_tiles = (d.Cout + BN - 1) / BN;
+  s.n_chunks = s.n_tiles;
+  s.tiles_per_chunk = 1;
+  s.conv = ConvGeom{1, tiles_w, d.stride, d.pad, d.ksize, cin_blocks};
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  LB_TRY(make_map_nhwc(&ma_hi, in.hi, d.Cin, d.W_in, d.H_in, d.N, in.ld, d.stride));
+  LB_TRY(make_map_nhwc(&ma_lo, in.lo, d.Cin, d.W_in, d.H_in, d.N, in.ld, d.stride));
+  LB_TRY(make_map(&mb_hi, wgt.hi, s.K, d.Cout, 1, wgt.ld, 0, BN));
+  LB_TRY(make_map(&mb_lo, wgt.lo, s.K, d.Cout, 1, wgt.ld, 0, BN));
+  typename Epi::Params ep = ep_in;
+  ep.H_out = d.H_out;
+  ep.W_out = d.W_out;
+  ep.tiles_w = tiles_w;
+  using S = GemmSmem<BN>;
+  constexpr int smem_bytes = S::kRingBytes + S::kBarBytes + Epi::kSmemBytes + 1024;
+  static_assert(smem_bytes <= 232448, "shared memory budget exceeded");
+  auto kern = gemm_split_kernel<BN, Epi>;
+  static bool configured[kMaxDevices] = {false};
+  int dev = 0;
+  LB_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev]) {
+    LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured[dev] = true;
+  }
+  const long items = static_cast<long>(s.batches) * s.m_tiles * s.n_chunks;
+  const int grid = static_cast<int>(items < sms ? items : sms);
+  TimingRec rec{nullptr, nullptr, TAG_CONV};
   if (g_timing) {
     LB_CUDA(cudaEventCreate(&rec.e0));
     LB_CUDA(cudaEventCreate(&rec.e1));
@@ -262,6 +347,80 @@ static int tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, const Lb
                          long x_base, long x_rows, int x_group_rows, long s_base, long s_rows, int s_group_rows,
                          int n_groups_x, bool self_pass, cudaStream_t stream);
 
+
+// ------------------------------------------------------------------------------------------------ backbone
+// ResNetFPN_8_2 forward (reference src/loftr/backbone/resnet_fpn.py:43-118) on tensor cores: every 3x3 / 1x1
+// convolution is an implicit GEMM through gemm_split_kernel<., EpiConv> (BatchNorm, ReLU / LeakyReLU, residual
+// add and the FPN upsample-add fused in the epilogue); activations live as NHWC fp16 hi/lo planes.
+struct BbBuf {
+  __half* hi;
+  __half* lo;
+  int ld;
+};
+static inline int pad8(int c) { return (c + 7) & ~7; }
+static BbBuf bb_take(Bump& b, long pixels, int C) {
+  BbBuf r;
+  r.ld = pad8(C);
+  r.hi = b.take<__half>(static_cast<size_t>(pixels) * r.ld);
+  r.lo = b.take<__half>(static_cast<size_t>(pixels) * r.ld);
+  return r;
+}
+struct BbWs {
+  BbBuf s0, t1, a1, x1;                 // 1/2 resolution, d1 channels
+  BbBuf t2, dn2, a2, x2;                // 1/4, d2
+  BbBuf t3, dn3, a3, x3, x3o;           // 1/8, d3
+  BbBuf x2l, m2, x2o;                   // 1/4: d3, d3, d2
+  BbBuf x1l, m1;                        // 1/2: d2, d2
+};
+static void carve_bb(Bump& b, BbWs& w, int N, int H, int W, int d1, int d2, int d3) {
+  const long p2 = static_cast<long>(N) * (H / 2) * (W / 2), p4 = static_cast<long>(N) * (H / 4) * (W / 4),
+             p8 = static_cast<long>(N) * (H / 8) * (W / 8);
+  w.s0 = bb_take(b, p2, d1); w.t1 = bb_take(b, p2, d1); w.a1 = bb_take(b, p2, d1); w.x1 = bb_take(b, p2, d1);
+  w.t2 = bb_take(b, p4, d2); w.dn2 = bb_take(b, p4, d2); w.a2 = bb_take(b, p4, d2); w.x2 = bb_take(b, p4, d2);
+  w.t3 = bb_take(b, p8, d3); w.dn3 = bb_take(b, p8, d3); w.a3 = bb_take(b, p8, d3); w.x3 = bb_take(b, p8, d3);
+  w.x3o = bb_take(b, p8, d3);
+  w.x2l = bb_take(b, p4, d3); w.m2 = bb_take(b, p4, d3); w.x2o = bb_take(b, p4, d2);
+  w.x1l = bb_take(b, p2, d2); w.m1 = bb_take(b, p2, d2);
+}
+
+struct ConvRun {
+  const LbConvWeights* w;
+  BbBuf in;
+  int H_in, W_in;
+  int act;
+  const BbBuf* res;
+  const BbBuf* up;
+  int up_h, up_w;
+  const BbBuf* out;
+  float* out_f32;
+  int f32_ld;
+};
+static int run_conv(const ConvRun& r, int N, cudaStream_t st) {
+  const LbConvWeights& w = *r.w;
+  ConvDesc d;
+  d.N = N; d.H_in = r.H_in; d.W_in = r.W_in; d.Cin = w.cin;
+  d.ksize = w.ksize; d.stride = w.stride; d.pad = w.ksize / 2;
+  d.H_out = (r.H_in + 2 * d.pad - w.ksize) / w.stride + 1;
+  d.W_out = (r.W_in + 2 * d.pad - w.ksize) / w.stride + 1;
+  d.Cout = w.cout;
+  const int cin_blocks = (w.cin + kBlockK - 1) / kBlockK;
+  Planes in{r.in.hi, r.in.lo, r.in.ld, 0};
+  Planes wg{w.w_hi, w.w_lo, static_cast<long>(w.ksize) * w.ksize * cin_blocks * kBlockK, 0};
+  if (w.cout <= 128) {
+    EpiConv<128>::Params ep{w.scale, w.shift, r.act, r.res ? r.res->hi : nullptr, r.res ? r.res->lo : nullptr,
+                            r.res ? r.res->ld : 0, r.up ? r.up->hi : nullptr, r.up ? r.up->lo : nullptr,
+                            r.up ? r.up->ld : 0, r.up_h, r.up_w, r.out ? r.out->hi : nullptr,
+                            r.out ? r.out->lo : nullptr, r.out ? r.out->ld : 0, r.out_f32, r.f32_ld, 0, 0, 0};
+    return launch_conv<128>(in, wg, d, ep, st);
+  }
+  if (w.cout > 256) return fail("convolutions with more than 256 output channels are not built");
+  EpiConv<256>::Params ep{w.scale, w.shift, r.act, r.res ? r.res->hi : nullptr, r.res ? r.res->lo : nullptr,
+                          r.res ? r.res->ld : 0, r.up ? r.up->hi : nullptr, r.up ? r.up->lo : nullptr,
+                          r.up ? r.up->ld : 0, r.up_h, r.up_w, r.out ? r.out->hi : nullptr,
+                          r.out ? r.out->lo : nullptr, r.out ? r.out->ld : 0, r.out_f32, r.f32_ld, 0, 0, 0};
+  return launch_conv<256>(in, wg, d, ep, st);
+}
+
 }  // namespace lb
 
 using namespace lb;
@@ -284,17 +443,17 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
     if (self_pass) {
       Planes A{cat_hi + x_base * ldc, cat_lo + x_base * ldc, ldc, 0};
       Planes B{lw.wqkv_hi, lw.wqkv_lo, C, 0};
-      typename Epi::Params ep{w.qkv + x_base * 3 * C, 3 * C, 2 * C, mask ? mask + x_base : nullptr, nullptr, 0};
+      typename Epi::Params ep{w.qkv + x_base * 3 * C, 3 * C, 2 * C, mask ? mask + x_base : nullptr, lw.s_qkv};
       LB_TRY((launch_gemm<BN, Epi>(TAG_PROJ, A, B, 1, static_cast<int>(x_rows), 3 * C, C, 0, ep, stream)));
     } else {
       Planes Aq{cat_hi + x_base * ldc, cat_lo + x_base * ldc, ldc, 0};
       Planes Bq{lw.wqkv_hi, lw.wqkv_lo, C, 0};
-      typename Epi::Params eq{w.qkv + x_base * 3 * C, 3 * C, C, mask ? mask + x_base : nullptr, nullptr, 0};
+      typename Epi::Params eq{w.qkv + x_base * 3 * C, 3 * C, C, mask ? mask + x_base : nullptr, lw.s_qkv};
       LB_TRY((launch_gemm<BN, Epi>(TAG_PROJ, Aq, Bq, 1, static_cast<int>(x_rows), C, C, 0, eq, stream)));
       Planes Ak{cat_hi + s_base * ldc, cat_lo + s_base * ldc, ldc, 0};
       Planes Bk{static_cast<const __half*>(lw.wqkv_hi) + static_cast<long>(C) * C,
                 static_cast<const __half*>(lw.wqkv_lo) + static_cast<long>(C) * C, C, 0};
-      typename Epi::Params ek{w.qkv + s_base * 3 * C + C, 3 * C, C, mask ? mask + s_base : nullptr, nullptr, 0};
+      typename Epi::Params ek{w.qkv + s_base * 3 * C + C, 3 * C, C, mask ? mask + s_base : nullptr, lw.s_qkv};
       LB_TRY((launch_gemm<BN, Epi>(TAG_PROJ, Ak, Bk, 1, static_cast<int>(s_rows), 2 * C, C, 0, ek, stream)));
     }
   }
@@ -333,7 +492,7 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
     Planes B{lw.wm_hi, lw.wm_lo, C, 0};
     typename Epi::Params ep{lw.ln1_g, lw.ln1_b, 1e-5f, nullptr, 0, nullptr, 0,
                             static_cast<__half*>(st.cat_hi) + x_base * ldc,
-                            static_cast<__half*>(st.cat_lo) + x_base * ldc, static_cast<int>(ldc), C};
+                            static_cast<__half*>(st.cat_lo) + x_base * ldc, static_cast<int>(ldc), C, lw.s_m};
     LB_TRY((launch_gemm<BN, Epi>(TAG_MERGE_LN, A, B, 1, static_cast<int>(x_rows), C, C, 0, ep, stream)));
   }
   // 5. mlp[0] + ReLU on cat([x, message]) -> h planes           [transformer.py:55, mlp 22-26]
@@ -342,7 +501,7 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
     Planes A{cat_hi + x_base * ldc, cat_lo + x_base * ldc, ldc, 0};
     Planes B{lw.w1_hi, lw.w1_lo, 2 * C, 0};
     typename Epi::Params ep{1, nullptr, 1, nullptr, 0, w.h_hi + x_base * ldc, w.h_lo + x_base * ldc,
-                            static_cast<int>(ldc), 0};
+                            static_cast<int>(ldc), 0, lw.s_1};
     LB_TRY((launch_gemm<BN, Epi>(TAG_MLP1, A, B, 1, static_cast<int>(x_rows), 2 * C, 2 * C, 0, ep, stream)));
   }
   // 6. mlp[2] + norm2 + residual -> x_f32 and cat[:, 0:C]        [transformer.py:55-58]
@@ -353,7 +512,7 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
     float* xf = st.x_f32 + x_base * C;
     typename Epi::Params ep{lw.ln2_g, lw.ln2_b, 1e-5f, xf, C, xf, C,
                             static_cast<__half*>(st.cat_hi) + x_base * ldc,
-                            static_cast<__half*>(st.cat_lo) + x_base * ldc, static_cast<int>(ldc), 0};
+                            static_cast<__half*>(st.cat_lo) + x_base * ldc, static_cast<int>(ldc), 0, lw.s_2};
     LB_TRY((launch_gemm<BN, Epi>(TAG_MLP2_LN, A, B, 1, static_cast<int>(x_rows), C, 2 * C, 0, ep, stream)));
   }
   return 0;
@@ -421,15 +580,15 @@ int lb_gemm_split(const void* a_hi, const void* a_lo, long lda, long a_batch_str
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (N % 256 == 0 || N > 128) {
     using Epi = EpiActStore<256>;
-    Epi::Params ep{out, static_cast<int>(ldo), 0, nullptr, nullptr, 0};
+    Epi::Params ep{out, static_cast<int>(ldo), 0, nullptr, 1.f};
     return launch_gemm<256, Epi>(TAG_GEMM_TEST, A, B, batches, M, N, K, 0, ep, st);
   }
   using Epi = EpiActStore<128>;
-  Epi::Params ep{out, static_cast<int>(ldo), 0, nullptr, nullptr, 0};
+  Epi::Params ep{out, static_cast<int>(ldo), 0, nullptr, 1.f};
   return launch_gemm<128, Epi>(TAG_GEMM_TEST, A, B, batches, M, N, K, 0, ep, st);
 }
 
-int lb_coarse_prep(const float* feat_nchw, const float* pe, int n_img, int C, int h, int w, int pe_h, int pe_w,
+int lb_coarse_prep(const float* feat, int nhwc, const float* pe, int n_img, int C, int h, int w, int pe_h, int pe_w,
                    float* x_f32, void* cat_hi, void* cat_lo, void* stream) {
   int sms;
   if (n_img <= 0) return 0;
@@ -439,7 +598,7 @@ int lb_coarse_prep(const float* feat_nchw, const float* pe, int n_img, int C, in
   if (n_img <= 0) return 0;
   dim3 grid(cdiv(static_cast<long>(h) * w, 32), cdiv(C, 32), n_img);
   coarse_prep_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
-      feat_nchw, pe, C, h, w, pe_h, pe_w, x_f32, static_cast<__half*>(cat_hi), static_cast<__half*>(cat_lo));
+      feat, nhwc, pe, C, h, w, pe_h, pe_w, x_f32, static_cast<__half*>(cat_hi), static_cast<__half*>(cat_lo));
   LB_LAUNCHED();
   return 0;
 }
@@ -495,6 +654,68 @@ int lb_transformer_forward(const LbEncoderLayerWeights* layers, const int* kinds
       return fail("unknown layer kind %d", kinds[l]);
     }
   }
+  return 0;
+}
+
+
+size_t lb_backbone_workspace_bytes(const LbBackboneWeights* w, int N, int H, int W) {
+  Bump b{nullptr, 0};
+  BbWs ws;
+  carve_bb(b, ws, N, H, W, w->l1[0].cout, w->l2[0].cout, w->l3[0].cout);
+  return b.off + 256;
+}
+
+int lb_backbone_forward(const LbBackboneWeights* w, const float* images, int N, int H, int W, float* feat_c_nhwc,
+                        float* feat_f_nhwc, void* ws, size_t ws_bytes, void* stream) {
+  int sms;
+  if (N <= 0) return 0;
+  LB_TRY(bind_device_of(images));
+  LB_TRY(device_check(&sms));
+  if (H % 8 != 0 || W % 8 != 0) return fail("image size %dx%d must be divisible by 8", H, W);
+  if (!ws) return fail("workspace pointer is null");
+  const int d1 = w->l1[0].cout, d2 = w->l2[0].cout, d3 = w->l3[0].cout;
+  if (w->stem_cout != 128 || d1 != w->stem_cout) return fail("backbone stem built for initial_dim = block_dims[0] = 128");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Bump b{static_cast<uint8_t*>(ws), ws_bytes};
+  BbWs B;
+  carve_bb(b, B, N, H, W, d1, d2, d3);
+  if (!b.ok) return fail("backbone workspace too small: need %zu bytes", lb_backbone_workspace_bytes(w, N, H, W));
+  const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8;
+
+  // stem: conv 7x7 s2 + BN + ReLU                                                  [resnet_fpn.py:101]
+  conv_stem7x7_kernel<128><<<dim3(cdiv(W2, 128), H2, N), 128, 0, st>>>(images, H, W, w->stem_wt, w->stem_scale,
+                                                                        w->stem_shift, B.s0.hi, B.s0.lo, B.s0.ld);
+  LB_LAUNCHED();
+  auto conv = [&](const LbConvWeights& cw, const BbBuf& in, int hin, int win, int act, const BbBuf* res,
+                  const BbBuf* up, int uph, int upw, const BbBuf* out, float* of32, int f32ld) -> int {
+    ConvRun r{&cw, in, hin, win, act, res, up, uph, upw, out, of32, f32ld};
+    return run_conv(r, N, st);
+  };
+  // layer1 (1/2)                                                                    [resnet_fpn.py:102]
+  LB_TRY(conv(w->l1[0], B.s0, H2, W2, 1, nullptr, nullptr, 0, 0, &B.t1, nullptr, 0));
+  LB_TRY(conv(w->l1[1], B.t1, H2, W2, 1, &B.s0, nullptr, 0, 0, &B.a1, nullptr, 0));
+  LB_TRY(conv(w->l1[2], B.a1, H2, W2, 1, nullptr, nullptr, 0, 0, &B.t1, nullptr, 0));
+  LB_TRY(conv(w->l1[3], B.t1, H2, W2, 1, &B.a1, nullptr, 0, 0, &B.x1, nullptr, 0));
+  // layer2 (1/4): first block strided with a projected skip                         [resnet_fpn.py:103]
+  LB_TRY(conv(w->l2[0], B.x1, H2, W2, 1, nullptr, nullptr, 0, 0, &B.t2, nullptr, 0));
+  LB_TRY(conv(w->l2_down, B.x1, H2, W2, 0, nullptr, nullptr, 0, 0, &B.dn2, nullptr, 0));
+  LB_TRY(conv(w->l2[1], B.t2, H4, W4, 1, &B.dn2, nullptr, 0, 0, &B.a2, nullptr, 0));
+  LB_TRY(conv(w->l2[2], B.a2, H4, W4, 1, nullptr, nullptr, 0, 0, &B.t2, nullptr, 0));
+  LB_TRY(conv(w->l2[3], B.t2, H4, W4, 1, &B.a2, nullptr, 0, 0, &B.x2, nullptr, 0));
+  // layer3 (1/8)                                                                    [resnet_fpn.py:104]
+  LB_TRY(conv(w->l3[0], B.x2, H4, W4, 1, nullptr, nullptr, 0, 0, &B.t3, nullptr, 0));
+  LB_TRY(conv(w->l3_down, B.x2, H4, W4, 0, nullptr, nullptr, 0, 0, &B.dn3, nullptr, 0));
+  LB_TRY(conv(w->l3[1], B.t3, H8, W8, 1, &B.dn3, nullptr, 0, 0, &B.a3, nullptr, 0));
+  LB_TRY(conv(w->l3[2], B.a3, H8, W8, 1, nullptr, nullptr, 0, 0, &B.t3, nullptr, 0));
+  LB_TRY(conv(w->l3[3], B.t3, H8, W8, 1, &B.a3, nullptr, 0, 0, &B.x3, nullptr, 0));
+  // FPN                                                                             [resnet_fpn.py:107-116]
+  LB_TRY(conv(w->l3_out, B.x3, H8, W8, 0, nullptr, nullptr, 0, 0, &B.x3o, feat_c_nhwc, d3));
+  LB_TRY(conv(w->l2_out, B.x2, H4, W4, 0, nullptr, &B.x3o, H8, W8, &B.x2l, nullptr, 0));
+  LB_TRY(conv(w->l2_out2[0], B.x2l, H4, W4, 2, nullptr, nullptr, 0, 0, &B.m2, nullptr, 0));
+  LB_TRY(conv(w->l2_out2[1], B.m2, H4, W4, 0, nullptr, nullptr, 0, 0, &B.x2o, nullptr, 0));
+  LB_TRY(conv(w->l1_out, B.x1, H2, W2, 0, nullptr, &B.x2o, H4, W4, &B.x1l, nullptr, 0));
+  LB_TRY(conv(w->l1_out2[0], B.x1l, H2, W2, 2, nullptr, nullptr, 0, 0, &B.m1, nullptr, 0));
+  LB_TRY(conv(w->l1_out2[1], B.m1, H2, W2, 0, nullptr, nullptr, 0, 0, nullptr, feat_f_nhwc, w->l1_out2[1].cout));
   return 0;
 }
 
@@ -772,7 +993,7 @@ int lb_fine_preprocess(const LbFinePreprocessArgs* a, void* ws, size_t ws_bytes,
   Planes A{win_hi, win_lo, a->Cf, 0};
   Planes B{a->merge_w_hi, a->merge_w_lo, a->Cf, 0};
   Epi::Params ep{0, gbias, WW, a->x_f32, a->Cf, static_cast<__half*>(a->cat_hi), static_cast<__half*>(a->cat_lo),
-                 2 * a->Cf, 0};
+                 2 * a->Cf, 0, a->merge_acc_scale};
   return launch_gemm<128, Epi>(TAG_FINE_MERGE, A, B, 1, static_cast<int>(rows), a->Cf, a->Cf, 0, ep, st);
 }
 

@@ -75,8 +75,7 @@ struct EpiActStore {
     int ld;
     int elu_cols;            // columns [0, elu_cols) get elu+1
     const uint8_t* rowmask;  // optional [batches*M] (1 = valid)
-    const uint8_t* rowmask2; // optional second mask applied to columns >= mask2_from (cross: never used)
-    int mask2_from;
+    float acc_scale;         // 2^-e: undoes the power-of-two pre-scaling of the weight planes (exact)
   };
   static constexpr int kSmemBytes = 0;
   const Params& p;
@@ -97,6 +96,8 @@ struct EpiActStore {
       if (col >= s.N) break;  // warp-uniform
       float x[32];
       load_acc32(tmem_acc, c * 32, x);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] *= p.acc_scale;
       if (col < p.elu_cols) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = x[j] > 0.f ? x[j] + 1.f : expf(x[j]);
@@ -125,6 +126,7 @@ struct EpiLayerNorm {
     __half* out_lo;
     int ld_pl;
     int pl_col0;
+    float acc_scale;        // 2^-e of the weight planes
   };
   static constexpr int kSmemBytes = 2 * BLOCK_N * 4 + 2 * 128 * 4;
   const Params& p;
@@ -167,7 +169,7 @@ struct EpiLayerNorm {
 #pragma unroll
       for (int j = 0; j < 32; ++j) sum += x[j];
     }
-    const float mean = row_total(sum) * (1.f / BLOCK_N);
+    const float mean = row_total(sum * p.acc_scale) * (1.f / BLOCK_N);
     float sq = 0.f;
 #pragma unroll 1
     for (int c = c_begin; c < c_end; ++c) {
@@ -175,7 +177,7 @@ struct EpiLayerNorm {
       load_acc32(tmem_acc, c * 32, x);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float d = x[j] - mean;
+        const float d = x[j] * p.acc_scale - mean;
         sq += d * d;
       }
     }
@@ -185,7 +187,7 @@ struct EpiLayerNorm {
       float x[32];
       load_acc32(tmem_acc, c * 32, x);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = (x[j] - mean) * rstd * sg[c * 32 + j] + sb[c * 32 + j];
+      for (int j = 0; j < 32; ++j) x[j] = (x[j] * p.acc_scale - mean) * rstd * sg[c * 32 + j] + sb[c * 32 + j];
       if (row_ok) {
         if (p.residual) {
           const float4* rp = reinterpret_cast<const float4*>(p.residual + grow * p.ld_res + c * 32);
@@ -225,6 +227,7 @@ struct EpiPlanes {
     __half* out_lo;
     int ld_pl;
     int pl_col0;
+    float acc_scale;      // 2^-e of the weight planes
   };
   static constexpr int kSmemBytes = 0;
   const Params& p;
@@ -245,6 +248,8 @@ struct EpiPlanes {
       if (col >= s.N) break;
       float x[32];
       load_acc32(tmem_acc, c * 32, x);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] *= p.acc_scale;
       if (p.relu) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
@@ -268,6 +273,165 @@ struct EpiPlanes {
         }
       }
     }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Convolution epilogue (backbone, reference src/loftr/backbone/resnet_fpn.py): the accumulator row r of tile
+// (ty, tx) is output pixel (ty*8 + r/16, tx*16 + r%16).
+//   y = acc * scale[c] + shift[c]            eval-mode BatchNorm folded to an affine map (BasicBlock :28-40)
+//   y += residual[pixel, c]                  BasicBlock skip connection (:35-40)
+//   y += bilinear_x2(up_src)[pixel, c]       FPN top-down merge, F.interpolate(scale_factor=2, bilinear,
+//                                            align_corners=True) (:107-113)
+//   y = relu / leaky_relu(0.01) / identity
+// written as NHWC fp16 planes (the next convolution's A operand) and / or NHWC fp32.
+__device__ __forceinline__ void load_planes32(const __half* hp, const __half* lp, float (&x)[32]) {
+  const uint4* h4 = reinterpret_cast<const uint4*>(hp);
+  const uint4* l4 = reinterpret_cast<const uint4*>(lp);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 a = h4[j], b = l4[j];
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&aw[k]));
+      const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&bw[k]));
+      x[j * 8 + 2 * k] = fh.x + fl.x;
+      x[j * 8 + 2 * k + 1] = fh.y + fl.y;
+    }
+  }
+}
+
+template <int BLOCK_N>
+struct EpiConv {
+  struct Params {
+    const float* scale;   // [N]
+    const float* shift;   // [N]
+    int act;              // 0 none, 1 relu, 2 leaky relu (0.01)
+    const __half* res_hi; // optional residual planes, NHWC, same spatial size, row stride res_ld
+    const __half* res_lo;
+    int res_ld;
+    const __half* up_hi;  // optional x2-upsample source planes [batches, up_h, up_w, up_ld]
+    const __half* up_lo;
+    int up_ld, up_h, up_w;
+    __half* out_hi;       // optional NHWC planes [batches*H*W, out_ld]
+    __half* out_lo;
+    int out_ld;
+    float* out_f32;       // optional NHWC fp32 [batches*H*W, f32_ld]
+    int f32_ld;
+    int H_out, W_out, tiles_w;
+  };
+  static constexpr int kSmemBytes = 2 * BLOCK_N * 4;
+  const Params& p;
+  const GemmShape& s;
+  float* s_scale;
+  float* s_shift;
+  __device__ EpiConv(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_) {
+    s_scale = reinterpret_cast<float*>(smem);
+    s_shift = s_scale + BLOCK_N;
+  }
+  __device__ void item_begin(int, int, int) {}
+  __device__ void item_end(int, int, int) {}
+  __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
+    const int t = epi_tid();
+    for (int j = t; j < BLOCK_N; j += kEpiThreads) {
+      const int c = n0 + j;
+      s_scale[j] = c < s.N ? p.scale[c] : 0.f;
+      s_shift[j] = c < s.N ? p.shift[c] : 0.f;
+    }
+    epi_bar_sync();
+    const int row = epi_row();
+    const int mt = m0 / kBlockM;
+    const int ty = mt / p.tiles_w, tx = mt - ty * p.tiles_w;
+    const int y = ty * kConvTileH + row / kConvTileW;
+    const int x = tx * kConvTileW + row % kConvTileW;
+    const bool ok = y < p.H_out && x < p.W_out;
+    const long pix = (static_cast<long>(batch) * p.H_out + y) * p.W_out + x;
+    // bilinear source coordinates (PyTorch upsample_bilinear2d, align_corners=True)
+    long u00 = 0, u01 = 0, u10 = 0, u11 = 0;
+    float wy1 = 0.f, wx1 = 0.f;
+    if (p.up_hi && ok) {
+      const float sh = p.H_out > 1 ? static_cast<float>(p.up_h - 1) / static_cast<float>(p.H_out - 1) : 0.f;
+      const float sw = p.W_out > 1 ? static_cast<float>(p.up_w - 1) / static_cast<float>(p.W_out - 1) : 0.f;
+      const float fy = sh * y, fx = sw * x;
+      const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+      const int y1 = y0 + (y0 < p.up_h - 1 ? 1 : 0), x1 = x0 + (x0 < p.up_w - 1 ? 1 : 0);
+      wy1 = fy - y0;
+      wx1 = fx - x0;
+      const long base = static_cast<long>(batch) * p.up_h * p.up_w;
+      u00 = (base + static_cast<long>(y0) * p.up_w + x0) * p.up_ld;
+      u01 = (base + static_cast<long>(y0) * p.up_w + x1) * p.up_ld;
+      u10 = (base + static_cast<long>(y1) * p.up_w + x0) * p.up_ld;
+      u11 = (base + static_cast<long>(y1) * p.up_w + x1) * p.up_ld;
+    }
+    const int c_begin = epi_half() * (BLOCK_N / 64);
+#pragma unroll 1
+    for (int c = c_begin; c < c_begin + BLOCK_N / 64; ++c) {
+      const int col = n0 + c * 32;
+      if (col >= s.N) break;
+      float v[32];
+      load_acc32(tmem_acc, c * 32, v);
+      if (!ok) continue;
+      const int nvalid = min(32, s.N - col);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], s_scale[c * 32 + j], s_shift[c * 32 + j]);
+      if (nvalid == 32) {
+        if (p.res_hi) {
+          float r[32];
+          load_planes32(p.res_hi + pix * p.res_ld + col, p.res_lo + pix * p.res_ld + col, r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += r[j];
+        }
+        if (p.up_hi) {
+          float a[32], b[32];
+          load_planes32(p.up_hi + u00 + col, p.up_lo + u00 + col, a);
+          load_planes32(p.up_hi + u01 + col, p.up_lo + u01 + col, b);
+          const float wy0 = 1.f - wy1, wx0 = 1.f - wx1;
+          float top[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) top[j] = wx0 * a[j] + wx1 * b[j];
+          load_planes32(p.up_hi + u10 + col, p.up_lo + u10 + col, a);
+          load_planes32(p.up_hi + u11 + col, p.up_lo + u11 + col, b);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += wy0 * top[j] + wy1 * (wx0 * a[j] + wx1 * b[j]);
+        }
+      } else {
+        // channel tail (e.g. 196 = 6*32 + 4): scalar path
+        const float wy0 = 1.f - wy1, wx0 = 1.f - wx1;
+        for (int j = 0; j < nvalid; ++j) {
+          if (p.res_hi) {
+            const long o = pix * p.res_ld + col + j;
+            v[j] += __half2float(p.res_hi[o]) + __half2float(p.res_lo[o]);
+          }
+          if (p.up_hi) {
+            auto at = [&](long o) { return __half2float(p.up_hi[o + col + j]) + __half2float(p.up_lo[o + col + j]); };
+            v[j] += wy0 * (wx0 * at(u00) + wx1 * at(u01)) + wy1 * (wx0 * at(u10) + wx1 * at(u11));
+          }
+        }
+      }
+      if (p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (p.act == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.01f * v[j];
+      }
+      if (nvalid == 32) {
+        if (p.out_f32) store_f32x32(p.out_f32 + pix * p.f32_ld + col, v);
+        if (p.out_hi) store_planes32(p.out_hi + pix * p.out_ld + col, p.out_lo + pix * p.out_ld + col, v);
+      } else {
+        for (int j = 0; j < nvalid; ++j) {
+          if (p.out_f32) p.out_f32[pix * p.f32_ld + col + j] = v[j];
+          if (p.out_hi) {
+            __half hh, ll;
+            split_f16(v[j], hh, ll);
+            p.out_hi[pix * p.out_ld + col + j] = hh;
+            p.out_lo[pix * p.out_ld + col + j] = ll;
+          }
+        }
+      }
+    }
+    epi_bar_sync();  // s_scale / s_shift are rewritten by the next tile
   }
 };
 

@@ -30,6 +30,20 @@ constexpr int kGemmThreads = 384;
 constexpr int kEpiThreads = 256;  // two epilogue warpgroups: rows x {left, right} half of the tile's columns
 constexpr int kEpiWarp0 = 4;
 
+// Implicit-GEMM convolution mode: the A operand is an NHWC activation (fp16 planes) read through a 4-D tensor
+// map; a 128-row tile is an 8 x 16 patch of output pixels and k-block kb = (tap, 64-channel block) is the same
+// patch shifted by the tap offset (out-of-image reads are zero-filled by TMA = the convolution's padding).
+constexpr int kConvTileH = 8;
+constexpr int kConvTileW = 16;
+struct ConvGeom {
+  int enabled;     // 0: plain GEMM (3-D maps)
+  int tiles_w;     // spatial tiles per tile row; m_tile = ty * tiles_w + tx
+  int stride;      // 1 or 2 (also encoded as the map's element stride)
+  int pad;
+  int taps_w;      // kernel width (taps = K / 64 / cin_blocks)
+  int cin_blocks;  // ceil(Cin / 64)
+};
+
 struct GemmShape {
   int batches;      // independent problems along the tensor maps' 3rd dimension
   int M;            // rows of A per batch
@@ -40,6 +54,7 @@ struct GemmShape {
   int n_tiles;      // ceil(N / BLOCK_N)
   int n_chunks;     // a work item = (batch, m_tile, chunk); chunk = tiles_per_chunk consecutive n tiles
   int tiles_per_chunk;
+  ConvGeom conv;
 };
 
 template <int BLOCK_N>
@@ -125,8 +140,19 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = ring + stage * S::kStageBytes;
             mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-            tma_load_3d(st, &tm_a_hi, &full_bar[stage], kb * kBlockK, mt * kBlockM, batch);
-            tma_load_3d(st + S::kATile, &tm_a_lo, &full_bar[stage], kb * kBlockK, mt * kBlockM, batch);
+            if (shape.conv.enabled) {
+              const ConvGeom& g = shape.conv;
+              const int tap = kb / g.cin_blocks, cb = kb - tap * g.cin_blocks;
+              const int ky = tap / g.taps_w, kx = tap - ky * g.taps_w;
+              const int ty = mt / g.tiles_w, tx = mt - ty * g.tiles_w;
+              const int x = tx * kConvTileW * g.stride + kx - g.pad;
+              const int y = ty * kConvTileH * g.stride + ky - g.pad;
+              tma_load_4d(st, &tm_a_hi, &full_bar[stage], cb * kBlockK, x, y, batch);
+              tma_load_4d(st + S::kATile, &tm_a_lo, &full_bar[stage], cb * kBlockK, x, y, batch);
+            } else {
+              tma_load_3d(st, &tm_a_hi, &full_bar[stage], kb * kBlockK, mt * kBlockM, batch);
+              tma_load_3d(st + S::kATile, &tm_a_lo, &full_bar[stage], kb * kBlockK, mt * kBlockM, batch);
+            }
             const int bb = shape.b_batched ? batch : 0;
             tma_load_3d(st + 2 * S::kATile, &tm_b_hi, &full_bar[stage], kb * kBlockK, nt * BLOCK_N, bb);
             tma_load_3d(st + 2 * S::kATile + S::kBTile, &tm_b_lo, &full_bar[stage], kb * kBlockK,

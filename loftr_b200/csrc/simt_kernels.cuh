@@ -25,11 +25,11 @@ __global__ void split_planes_kernel(const float* __restrict__ x, long rows, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Coarse prologue: feat_c [n_img, C, h, w] (NCHW, backbone output) + pe[C, pe_h, pe_w] ->
-// token-major x_f32 [n_img*h*w, C] and fp16 planes in columns [0, C) of the [rows, 2C] cat buffer.
+// Coarse prologue: feat_c (backbone output, NCHW [n_img, C, h, w] or NHWC [n_img, h, w, C]) + pe[C, pe_h, pe_w]
+// -> token-major x_f32 [n_img*h*w, C] and fp16 planes in columns [0, C) of the [rows, 2C] cat buffer.
 // = PositionEncodingSine.forward + rearrange 'n c h w -> n (h w) c' (reference loftr.py:58-59,
 // position_encoding.py:37-42).  32x32 smem transpose so both sides are coalesced.
-__global__ void coarse_prep_kernel(const float* __restrict__ feat, const float* __restrict__ pe, int C,
+__global__ void coarse_prep_kernel(const float* __restrict__ feat, int nhwc, const float* __restrict__ pe, int C,
                                    int h, int w, int pe_h, int pe_w, float* __restrict__ x_f32,
                                    __half* __restrict__ cat_hi, __half* __restrict__ cat_lo) {
   __shared__ float tile[32][33];
@@ -37,14 +37,15 @@ __global__ void coarse_prep_kernel(const float* __restrict__ feat, const float* 
   const int img = blockIdx.z;
   const int l0 = blockIdx.x * 32;
   const int c0 = blockIdx.y * 32;
-  // read: threadIdx.x along l (contiguous in NCHW), threadIdx.y along c
+  // read: threadIdx.x along l (contiguous in the channel-major sources), threadIdx.y along c
   for (int cy = threadIdx.y; cy < 32; cy += blockDim.y) {
     const int c = c0 + cy;
     const int l = l0 + threadIdx.x;
     float v = 0.f;
     if (c < C && l < L) {
       const int y = l / w, x = l - y * w;
-      v = feat[(static_cast<long>(img) * C + c) * L + l] + pe[(static_cast<long>(c) * pe_h + y) * pe_w + x];
+      v = pe[(static_cast<long>(c) * pe_h + y) * pe_w + x];
+      if (!nhwc) v += feat[(static_cast<long>(img) * C + c) * L + l];
     }
     tile[cy][threadIdx.x] = v;
   }
@@ -54,14 +55,74 @@ __global__ void coarse_prep_kernel(const float* __restrict__ feat, const float* 
     const int l = l0 + ly;
     const int c = c0 + threadIdx.x;
     if (c < C && l < L) {
-      const float v = tile[threadIdx.x][ly];
       const long row = static_cast<long>(img) * L + l;
+      float v = tile[threadIdx.x][ly];
+      if (nhwc) v = feat[row * C + c] + v;
       x_f32[row * C + c] = v;
       __half hh, ll;
       split_f16(v, hh, ll);
       cat_hi[row * (2 * C) + c] = hh;
       cat_lo[row * (2 * C) + c] = ll;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backbone stem: conv 7x7 stride 2, 1 -> Cout channels, + folded BatchNorm + ReLU
+// (reference resnet_fpn.py:58-60,101), written as NHWC fp16 planes.  One thread per output pixel keeps all
+// 128 output channels in registers; the 49 x Cout weights sit in shared memory (broadcast reads).
+template <int COUT>
+__global__ void __launch_bounds__(128) conv_stem7x7_kernel(const float* __restrict__ img, int H, int W,
+                                                           const float* __restrict__ wt /*[49][COUT]*/,
+                                                           const float* __restrict__ scale,
+                                                           const float* __restrict__ shift,
+                                                           __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                                           int out_ld) {
+  __shared__ __align__(16) float s_w[49 * COUT];
+  __shared__ float s_sc[COUT], s_sh[COUT];
+  for (int i = threadIdx.x; i < 49 * COUT; i += blockDim.x) s_w[i] = wt[i];
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
+    s_sc[i] = scale[i];
+    s_sh[i] = shift[i];
+  }
+  __syncthreads();
+  const int Ho = H / 2, Wo = W / 2;
+  const int n = blockIdx.z;
+  const int oy = blockIdx.y;
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ox >= Wo) return;
+  float in[49];
+#pragma unroll
+  for (int ky = 0; ky < 7; ++ky) {
+    const int iy = oy * 2 + ky - 3;
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) {
+      const int ix = ox * 2 + kx - 3;
+      in[ky * 7 + kx] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? img[(static_cast<long>(n) * H + iy) * W + ix] : 0.f;
+    }
+  }
+  const long pix = (static_cast<long>(n) * Ho + oy) * Wo + ox;
+#pragma unroll 1
+  for (int c0 = 0; c0 < COUT; c0 += 32) {
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 49; ++t) {
+      const float v = in[t];
+      const float4* wp = reinterpret_cast<const float4*>(&s_w[t * COUT + c0]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 w4 = wp[j];
+        acc[4 * j] = fmaf(v, w4.x, acc[4 * j]);
+        acc[4 * j + 1] = fmaf(v, w4.y, acc[4 * j + 1]);
+        acc[4 * j + 2] = fmaf(v, w4.z, acc[4 * j + 2]);
+        acc[4 * j + 3] = fmaf(v, w4.w, acc[4 * j + 3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = fmaxf(fmaf(acc[j], s_sc[c0 + j], s_sh[c0 + j]), 0.f);
+    store_planes32(out_hi + pix * out_ld + c0, out_lo + pix * out_ld + c0, acc);
   }
 }
 

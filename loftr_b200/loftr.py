@@ -31,6 +31,18 @@ def _require_cuda(t: torch.Tensor, name: str):
                            "no CPU implementation")
 
 
+def split_weight(w: torch.Tensor):
+    """Weight matrix -> (hi, lo, acc_scale): planes of w * 2^e with e chosen so that max|w| * 2^e ~ 2^12, and
+    acc_scale = 2^-e for the epilogue.  Power-of-two scaling is exact; it moves the `lo` residuals of typical
+    (small) weights out of fp16's subnormal range, where they would only carry ~1e-6 relative accuracy."""
+    w = w.detach().float().contiguous()
+    amax = float(w.abs().max())
+    e = 0 if amax == 0.0 else int(math.floor(math.log2(4096.0 / amax)))
+    e = max(min(e, 24), -24)
+    hi, lo = split_planes((w * (2.0 ** e)).contiguous())
+    return hi, lo, 2.0 ** (-e)
+
+
 def split_planes(x: torch.Tensor, hi: torch.Tensor | None = None, lo: torch.Tensor | None = None, col0: int = 0):
     """fp32 [rows, cols] -> fp16 hi/lo planes via the library kernel (x ~= hi + lo)."""
     assert x.dim() == 2 and x.dtype == torch.float32
@@ -44,6 +56,91 @@ def split_planes(x: torch.Tensor, hi: torch.Tensor | None = None, lo: torch.Tens
     _lib.check(lib.lb_split_planes(x.data_ptr(), rows, cols, x.stride(0), hi.data_ptr(), lo.data_ptr(), hi.stride(0),
                                    col0, _stream()))
     return hi, lo
+
+
+class TensorCoreBackbone:
+    """ResNetFPN_8_2 forward through `lb_backbone_forward` (implicit-GEMM convolutions on tcgen05).  Holds no
+    parameters of its own: it packs the weights of the PyTorch `ResNetFPN` module it wraps (BatchNorm folded
+    with its running statistics = eval mode), lazily and again whenever a parameter or buffer changes."""
+
+    def __init__(self, torch_backbone):
+        self.m = torch_backbone
+        self._packed = None
+        self._key = None
+
+    @staticmethod
+    def supported(torch_backbone) -> bool:
+        m = torch_backbone
+        return getattr(m, "depth", 0) == 3 and m.conv1.out_channels == 128 and m.layer1[0].conv1.out_channels == 128 \
+            and max(m.layer2[0].conv1.out_channels, m.layer3[0].conv1.out_channels) <= 256
+
+    @staticmethod
+    def _fold(bn, cout, device):
+        if bn is None:
+            return torch.ones(cout, device=device), torch.zeros(cout, device=device)
+        scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+        shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+        return scale.contiguous(), shift.contiguous()
+
+    def _conv(self, conv, bn, keep):
+        w = conv.weight.detach().float()                      # [cout, cin, k, k]
+        cout, cin, k, _ = w.shape
+        cb = -(-cin // 64) * 64
+        wp = torch.zeros(cout, k * k, cb, device=w.device)
+        wp[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, k * k, cin)   # tap-major, channels padded per tap
+        hi, lo, acc_scale = split_weight(wp.reshape(cout, k * k * cb))
+        scale, shift = self._fold(bn, cout, w.device)
+        scale = (scale * acc_scale).contiguous()   # y = acc * (2^-e * bn_scale) + bn_shift
+        keep += [hi, lo, scale, shift]
+        return _lib.LbConvWeights(hi.data_ptr(), lo.data_ptr(), scale.data_ptr(), shift.data_ptr(), cin, cout, k,
+                                  conv.stride[0])
+
+    def _pack(self):
+        m = self.m
+        tensors = list(m.parameters()) + list(m.buffers())
+        key = tuple(t._version for t in tensors) + tuple(t.data_ptr() for t in tensors)
+        if self._packed is not None and self._key == key:
+            return self._packed
+        keep = []
+        w = _lib.LbBackboneWeights()
+        with torch.no_grad():
+            stem = m.conv1.weight.detach().float().reshape(m.conv1.out_channels, 49).t().contiguous()
+            sc, sh = self._fold(m.bn1, m.conv1.out_channels, stem.device)
+            keep += [stem, sc, sh]
+            w.stem_wt, w.stem_scale, w.stem_shift, w.stem_cout = stem.data_ptr(), sc.data_ptr(), sh.data_ptr(), stem.shape[1]
+            for name, layer in (("l1", m.layer1), ("l2", m.layer2), ("l3", m.layer3)):
+                arr = getattr(w, name)
+                for bi, blk in enumerate(layer):
+                    arr[2 * bi] = self._conv(blk.conv1, blk.bn1, keep)
+                    arr[2 * bi + 1] = self._conv(blk.conv2, blk.bn2, keep)
+                if layer[0].downsample is not None:
+                    setattr(w, name + "_down", self._conv(layer[0].downsample[0], layer[0].downsample[1], keep))
+            w.l3_out = self._conv(m.layer3_outconv, None, keep)
+            w.l2_out = self._conv(m.layer2_outconv, None, keep)
+            w.l2_out2[0] = self._conv(m.layer2_outconv2[0], m.layer2_outconv2[1], keep)
+            w.l2_out2[1] = self._conv(m.layer2_outconv2[3], None, keep)
+            w.l1_out = self._conv(m.layer1_outconv, None, keep)
+            w.l1_out2[0] = self._conv(m.layer1_outconv2[0], m.layer1_outconv2[1], keep)
+            w.l1_out2[1] = self._conv(m.layer1_outconv2[3], None, keep)
+        self._packed, self._key = (w, keep), key
+        return self._packed
+
+    @torch.no_grad()
+    def __call__(self, images):
+        """images [N, 1, H, W] fp32 (CUDA) -> (feat_c NHWC [N, H/8, W/8, C3], feat_f NHWC [N, H/2, W/2, C1])."""
+        _require_cuda(images, "images")
+        lib = _lib.load()
+        w, _ = self._pack()
+        images = images.float().contiguous()
+        n, _, h, wd = images.shape
+        c3, c1 = self.m.layer3_outconv.out_channels, self.m.layer1_outconv2[3].out_channels
+        feat_c = torch.empty(n, h // 8, wd // 8, c3, dtype=torch.float32, device=images.device)
+        feat_f = torch.empty(n, h // 2, wd // 2, c1, dtype=torch.float32, device=images.device)
+        nbytes = lib.lb_backbone_workspace_bytes(C.byref(w), n, h, wd)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=images.device)
+        _lib.check(lib.lb_backbone_forward(C.byref(w), images.data_ptr(), n, h, wd, feat_c.data_ptr(),
+                                           feat_f.data_ptr(), ws.data_ptr(), nbytes, _stream()))
+        return feat_c, feat_f
 
 
 class PositionEncodingSine(nn.Module):
@@ -128,8 +225,9 @@ class LocalFeatureTransformer(nn.Module):
         with torch.no_grad():
             for i, layer in enumerate(self.layers):
                 wqkv = torch.cat([layer.q_proj.weight, layer.k_proj.weight, layer.v_proj.weight], 0).float()
-                planes = [split_planes(wqkv), split_planes(layer.merge.weight.float()),
-                          split_planes(layer.mlp[0].weight.float()), split_planes(layer.mlp[2].weight.float())]
+                scaled = [split_weight(wqkv), split_weight(layer.merge.weight), split_weight(layer.mlp[0].weight),
+                          split_weight(layer.mlp[2].weight)]
+                planes = [(h, l) for h, l, _ in scaled]
                 lns = [layer.norm1.weight, layer.norm1.bias, layer.norm2.weight, layer.norm2.bias]
                 lns = [t.detach().float().contiguous() for t in lns]
                 keep.append((planes, lns))
@@ -137,6 +235,7 @@ class LocalFeatureTransformer(nn.Module):
                 (w.wqkv_hi, w.wqkv_lo), (w.wm_hi, w.wm_lo), (w.w1_hi, w.w1_lo), (w.w2_hi, w.w2_lo) = [
                     (h.data_ptr(), l.data_ptr()) for h, l in planes]
                 w.ln1_g, w.ln1_b, w.ln2_g, w.ln2_b = [t.data_ptr() for t in lns]
+                w.s_qkv, w.s_m, w.s_1, w.s_2 = [sc for _, _, sc in scaled]
         kinds = (C.c_int * len(self.layers))(*[_KIND[n] for n in self.layer_names])
         self._packed = (arr, kinds, keep)
         self._packed_key = key
@@ -287,12 +386,12 @@ class FinePreprocess(nn.Module):
         if self._packed is None or self._packed_key != key:
             with torch.no_grad():
                 wm = self.merge_feat.weight.detach().float().contiguous()
-                hi, lo = split_planes(wm[:, : self.d_model_f].contiguous())
+                hi, lo, msc = split_weight(wm[:, : self.d_model_f])
                 self._packed = {"wdt": self.down_proj.weight.detach().float().t().contiguous(),
                                 "bd": self.down_proj.bias.detach().float().contiguous(),
                                 "wm2t": wm[:, self.d_model_f:].t().contiguous(),
                                 "bm": self.merge_feat.bias.detach().float().contiguous(),
-                                "wm_hi": hi, "wm_lo": lo}
+                                "wm_hi": hi, "wm_lo": lo, "wm_scale": msc}
             self._packed_key = key
         return self._packed
 
@@ -321,7 +420,7 @@ class FinePreprocess(nn.Module):
         a.b_ids, a.i_ids, a.j_ids = data["b_ids"].data_ptr(), data["i_ids"].data_ptr(), data["j_ids"].data_ptr()
         a.down_wt, a.down_b, a.merge_w2t, a.merge_b = (p["wdt"].data_ptr(), p["bd"].data_ptr(), p["wm2t"].data_ptr(),
                                                        p["bm"].data_ptr())
-        a.merge_w_hi, a.merge_w_lo = p["wm_hi"].data_ptr(), p["wm_lo"].data_ptr()
+        a.merge_w_hi, a.merge_w_lo, a.merge_acc_scale = p["wm_hi"].data_ptr(), p["wm_lo"].data_ptr(), p["wm_scale"]
         a.x_f32, a.cat_hi, a.cat_lo = state.x.data_ptr(), state.cat_hi.data_ptr(), state.cat_lo.data_ptr()
         nbytes = lib.lb_fine_preprocess_workspace_bytes(m, W, cf)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -383,10 +482,21 @@ class FineMatching(nn.Module):
 class LoFTR(nn.Module):
     """Top-level matcher (reference loftr.py:12-81)."""
 
-    def __init__(self, config):
+    def __init__(self, config, backbone_impl="auto"):
+        """backbone_impl: "torch" keeps the PyTorch/cuDNN ResNet-FPN forward (the north_star default scope);
+        "b200" runs it as implicit-GEMM convolutions on the tensor cores; "auto" picks
+        "b200" whenever the configured backbone is the supported ResNetFPN_8_2 shape.  Both are GPU paths."""
         super().__init__()
         self.config = config
         self.backbone = build_backbone(config)
+        if backbone_impl == "auto":
+            backbone_impl = "b200" if TensorCoreBackbone.supported(self.backbone) else "torch"
+        if backbone_impl not in ("torch", "b200"):
+            raise ValueError(backbone_impl)
+        if backbone_impl == "b200" and not TensorCoreBackbone.supported(self.backbone):
+            raise ValueError("the tensor-core backbone is built for ResNetFPN_8_2 with initial_dim 128, dims <= 256")
+        self.backbone_impl = backbone_impl
+        self._tc_backbone = TensorCoreBackbone(self.backbone) if backbone_impl == "b200" else None
         self.pos_encoding = PositionEncodingSine(config["coarse"]["d_model"],
                                                  temp_bug_fix=config["coarse"]["temp_bug_fix"])
         self.loftr_coarse = LocalFeatureTransformer(config["coarse"])
@@ -408,8 +518,16 @@ class LoFTR(nn.Module):
         bs = img0.size(0)
         data.update({"bs": bs, "hw0_i": img0.shape[2:], "hw1_i": img1.shape[2:]})
 
-        # 1. local feature CNN (PyTorch)                                              [loftr.py:45-49]
-        if data["hw0_i"] == data["hw1_i"]:
+        # 1. local feature CNN                                                         [loftr.py:45-49]
+        nhwc = self._tc_backbone is not None
+        if nhwc:   # NHWC outputs; viewed as [N, C, H, W] tensors with channels-last strides
+            if data["hw0_i"] == data["hw1_i"]:
+                fc, ff = self._tc_backbone(torch.cat([img0, img1], dim=0))
+                (feat_c0, feat_c1), (feat_f0, feat_f1) = fc.split(bs), ff.split(bs)
+            else:
+                (feat_c0, feat_f0), (feat_c1, feat_f1) = self._tc_backbone(img0), self._tc_backbone(img1)
+            feat_c0, feat_c1, feat_f0, feat_f1 = (t.permute(0, 3, 1, 2) for t in (feat_c0, feat_c1, feat_f0, feat_f1))
+        elif data["hw0_i"] == data["hw1_i"]:
             feats_c, feats_f = self.backbone(torch.cat([img0, img1], dim=0))
             (feat_c0, feat_c1), (feat_f0, feat_f1) = feats_c.split(bs), feats_f.split(bs)
         else:
@@ -425,8 +543,9 @@ class LoFTR(nn.Module):
         pe = self.pos_encoding.pe[0]
         st = _stream()
         for feat, h, w, row0 in ((feat_c0, h0, w0, 0), (feat_c1, h1, w1, bs * L)):
-            feat = feat.float().contiguous()
-            _lib.check(lib.lb_coarse_prep(feat.data_ptr(), pe.data_ptr(), bs, c, h, w, pe.shape[1], pe.shape[2],
+            feat = feat.float()
+            feat = feat.permute(0, 2, 3, 1).contiguous() if nhwc else feat.contiguous()   # no copy in either case
+            _lib.check(lib.lb_coarse_prep(feat.data_ptr(), int(nhwc), pe.data_ptr(), bs, c, h, w, pe.shape[1], pe.shape[2],
                                           state.x.data_ptr() + row0 * c * 4,
                                           state.cat_hi.data_ptr() + row0 * 2 * c * 2,
                                           state.cat_lo.data_ptr() + row0 * 2 * c * 2, st))

@@ -5,6 +5,7 @@ mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 groups=(
   "tests/test_engine_gpu.py::test_gemm_split_matches_fp64"
+  "tests/test_engine_gpu.py::test_tensor_core_backbone_matches_torch"
   "tests/test_engine_gpu.py::test_transformer_matches_oracle"
   "tests/test_engine_gpu.py::test_coarse_matching_matches_reference_golden"
   "tests/test_engine_gpu.py::test_coarse_matching_full_size_vs_oracle"
@@ -18,6 +19,7 @@ groups=(
 )
 rc=0
 : > gpurun_out/gpu_tests.log
+rm -f gpurun_out/parity_stats.jsonl
 for g in "${groups[@]}"; do
   echo "=== $g" >> gpurun_out/gpu_tests.log
   timeout 600 python -m pytest "$g" -q -m gpu -x --no-header -p no:cacheprovider >> gpurun_out/gpu_tests.log 2>&1 || rc=1

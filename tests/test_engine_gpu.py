@@ -185,6 +185,7 @@ def test_end_to_end_matches_reference_golden(case):
     np.testing.assert_allclose(data["_feat_c0"].cpu().numpy()[:, ::7, ::5], gold["feat_c0_s"], rtol=1e-3, atol=1e-3)
     np.testing.assert_allclose(data["_feat_c1"].cpu().numpy()[:, ::7, ::5], gold["feat_c1_s"], rtol=1e-3, atol=1e-3)
     stats = util.compare_matches(got, gold, gold, conf_rtol=1e-3, px_tol=0.5, min_overlap=0.97, label=case["name"])
+    util.record("e2e_golden_" + case["name"], stats)
     m = len(gold["b_ids"])
     if m == 0:
         assert got["b_ids"].shape == (0,) and got["mkpts0_f"].shape == (0, 2) and got["expec_f"].shape == (0, 3)
@@ -206,7 +207,8 @@ def test_end_to_end_640x480_vs_oracle():
     stats = util.compare_matches(got, out, None, conf_rtol=1e-3, px_tol=0.5, min_overlap=0.99, label="640x480")
     err = np.abs(data["_feat_c0"].cpu().numpy() - out["feat_c0"]).max()
     assert err < 1e-3, f"coarse transformer output differs by {err:.3e}"
-    print("640x480 parity:", stats)
+    stats["feat_c0_max_abs_err"] = float(err)
+    util.record("e2e_640x480_ds_vs_oracle", stats)
 
 
 def test_no_cpu_fallback():
@@ -230,7 +232,7 @@ def test_outdoor_832_masked_vs_oracle():
     # nothing may come from the padded area or its border
     i, j = got["i_ids"], got["j_ids"]
     assert (i % 104 < 624 // 8 - 2).all() and (j // 104 < 640 // 8 - 2).all()
-    print("832x832 masked parity:", stats)
+    util.record("e2e_832x832_masked_vs_oracle", stats)
 
 
 def test_sinkhorn_640x480_vs_oracle():
@@ -243,7 +245,7 @@ def test_sinkhorn_640x480_vs_oracle():
                                               "mkpts1_f"]}
     assert len(out["b_ids"]) > 300
     stats = util.compare_matches(got, out, None, conf_rtol=1e-3, px_tol=0.5, min_overlap=0.99, label="ot 640x480")
-    print("sinkhorn 640x480 parity:", stats)
+    util.record("e2e_640x480_sinkhorn_vs_oracle", stats)
 
 
 @pytest.mark.parametrize("hw", [(240, 320), (960, 1280)])
@@ -294,3 +296,37 @@ def test_resolution_sweep_properties(hw):
     full_row_lse = torch.cat([torch.logsumexp((f0[a:a + 2048] @ f1.T) / 0.1, 1) for a in range(0, f0.shape[0], 2048)])
     col_key = 2 * sim_cols - full_row_lse[:, None]
     assert torch.equal(col_key.argmax(0), ii), "a reported match is not the column's nearest neighbour"
+
+
+# ------------------------------------------------------------------------------------------------ backbone on tensor cores
+@pytest.mark.parametrize("shape", [(2, 96, 128), (1, 480, 640), (1, 136, 200)])
+def test_tensor_core_backbone_matches_torch(shape):
+    """lb_backbone_forward (implicit-GEMM convolutions, folded BN, fused residual / FPN upsample-add) against the
+    PyTorch ResNetFPN_8_2 forward in fp32 (TF32 off) with non-trivial BatchNorm statistics."""
+    from loftr_b200.loftr import TensorCoreBackbone
+    n, h, w = shape
+    case = dict(CASES[0])
+    model, _, _ = util.build_model(case, DEV)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    rs = np.random.RandomState(4)
+    img = _t(rs.uniform(0, 1, (n, 1, h, w)).astype(np.float32))
+    import copy
+    with torch.no_grad():
+        ref_c, ref_f = model.backbone(img)
+        m64 = copy.deepcopy(model.backbone).double()
+        ex_c, ex_f = m64(img.double())          # fp64 ground truth: both fp32 paths are judged against it
+    tc = TensorCoreBackbone(model.backbone)
+    got_c, got_f = tc(img)
+    assert got_c.shape == (n, h // 8, w // 8, 256) and got_f.shape == (n, h // 2, w // 2, 128)
+    for got, ref, ex, name in ((got_c, ref_c, ex_c, "coarse"), (got_f, ref_f, ex_f, "fine")):
+        scale = ex.abs().max().item()
+        err_ours = (got.permute(0, 3, 1, 2).double() - ex).abs().max().item()
+        err_torch = (ref.double() - ex).abs().max().item()
+        util.record(f"backbone_{name}_{n}x{h}x{w}", {"err_ours_vs_fp64": err_ours, "err_torch_fp32_vs_fp64": err_torch,
+                                                      "scale": scale})
+        # The tensor-core path is less accurate than cuDNN's fp32 FMA chain (measured ~4e-5 vs ~1.5e-6 of the
+        # feature scale): tcgen05 accumulates in fp32 with truncation, once per MMA (K/16*3 adds per output), and
+        # the bias compounds over the ~20 convolutions.  It stays well inside what the matcher tolerances need
+        # (end-to-end mconf rel err 5e-4 < 1e-3, see parity_stats); bound it so regressions are caught.
+        assert err_ours <= 1e-4 * scale, f"{name}: {err_ours:.3e} (torch fp32: {err_torch:.3e}, scale {scale:.3e})"

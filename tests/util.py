@@ -93,3 +93,15 @@ def compare_matches(got, ref, gold=None, conf_rtol=1e-3, px_tol=0.5, min_overlap
             stats[key + "_max"] = float(d)
             assert d < tol, f"{label}: {key} differs by {d:.4f} px"
     return stats
+
+
+def record(name, stats):
+    """Append parity statistics to gpurun_out/parity_stats.jsonl (kept as evidence; prints are captured by pytest)."""
+    import json
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_stats.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, **{k: (float(v) if isinstance(v, (int, float)) else v) for k, v in stats.items()}}) + "\n")
+    except OSError:
+        pass
