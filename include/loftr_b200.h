@@ -165,6 +165,7 @@ typedef struct LbCoarseMatchArgs {
   float* mkpts0_c;        /* [capacity, 2] */
   float* mkpts1_c;
   int* count;             /* device int: number of matches M */
+  float* conf_matrix;     /* optional [n_pairs, L, S] fp32: the reference's data['conf_matrix'] (opt-in) */
 } LbCoarseMatchArgs;
 
 size_t lb_coarse_match_workspace_bytes(int n_pairs, int L, int S);

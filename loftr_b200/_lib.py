@@ -60,6 +60,7 @@ class LbCoarseMatchArgs(C.Structure):
         ("capacity", c_long),
         ("b_ids", c_void_p), ("i_ids", c_void_p), ("j_ids", c_void_p),
         ("mconf", c_void_p), ("mkpts0_c", c_void_p), ("mkpts1_c", c_void_p), ("count", c_void_p),
+        ("conf_matrix", c_void_p),
     ]
 
 

@@ -261,7 +261,7 @@ static int launch_conv(const Planes& in, const Planes& wgt, const ConvDesc& d, c
   using S = GemmSmem<BN>;
   constexpr int smem_bytes = S::kRingBytes + S::kBarBytes + Epi::kSmemBytes + 1024;
   static_assert(smem_bytes <= 232448, "shared memory budget exceeded");
-  auto kern = gemm_split_kernel<BN, Epi>;
+  auto kern = gemm_split_kernel<BN, Epi, true>;   // dual accumulator: EpiConv adds the correction accumulator
   static bool configured[kMaxDevices] = {false};
   int dev = 0;
   LB_CUDA(cudaGetDevice(&dev));
@@ -851,6 +851,12 @@ int lb_coarse_match(const LbCoarseMatchArgs* a, void* ws, size_t ws_bytes, void*
     LB_LAUNCHED();
     fill_kernel<<<cdiv(n, TB), TB, 0, st>>>(w.bin_v, 0.f, n);
     LB_LAUNCHED();
+    fill_kernel<<<cdiv(nl, TB), TB, 0, st>>>(w.row_u, 0.f, nl);   // u = 0 (only observable with skh_iters == 0)
+    LB_LAUNCHED();
+    fill_kernel<<<cdiv(n, TB), TB, 0, st>>>(w.bin_u, 0.f, n);
+    LB_LAUNCHED();
+    mask_term_kernel<<<cdiv(nl, TB), TB, 0, st>>>(nullptr, a->mask0, nullptr, nl, w.row_t);
+    LB_LAUNCHED();
     for (int it = 0; it < a->skh_iters; ++it) {
       // u_i = log_mu_i - LSE_j(Z_ij + v_j), j over S real columns + the dustbin column   [superglue.py:146]
       {
@@ -912,6 +918,13 @@ int lb_coarse_match(const LbCoarseMatchArgs* a, void* ws, size_t ws_bytes, void*
       row_dead = w.row_dead;
       col_dead = w.col_dead;
     }
+  }
+
+  if (a->conf_matrix) {   // opt-in materialisation of data['conf_matrix']         [coarse_matching.py:145]
+    using Epi = EpiConfStore<BN>;
+    // row_t / col_t hold -LSE (dual-softmax) or the Sinkhorn potentials, with padded / prefiltered entries disabled
+    Epi::Params ep{scale, alpha, conf_bias, w.row_t, w.col_t, a->conf_matrix};
+    LB_TRY((launch_gemm<BN, Epi>(TAG_SCORE_ARGMAX, A, B, n, L, S, C, 0, ep, st)));
   }
 
   SelectParams sp;

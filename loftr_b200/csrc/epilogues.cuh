@@ -371,6 +371,12 @@ struct EpiConv {
       if (col >= s.N) break;
       float v[32];
       load_acc32(tmem_acc, c * 32, v);
+      {  // dual accumulator: add the correction products (hi*lo + lo*hi), see gemm_split.cuh
+        float corr[32];
+        load_acc32(tmem_acc + BLOCK_N, c * 32, corr);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += corr[j];
+      }
       if (!ok) continue;
       const int nvalid = min(32, s.N - col);
 #pragma unroll
@@ -604,6 +610,64 @@ struct EpiScoreLse {
       }
     }
     epi_bar_sync();  // s_ct / s_cpart are reused by the next tile
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Optional materialisation of the confidence matrix (reference `data['conf_matrix']`, coarse_matching.py:145;
+// its only consumer is the training loss, so the engine writes it on request only):
+//   conf[i,j] = exp(alpha*z[i,j] + rowterm[i] + colterm[j] + bias), 0 where a term is disabled (padded /
+//   prefiltered rows and columns).  HBM-bound: 4*L*S bytes per pair.
+template <int BLOCK_N>
+struct EpiConfStore {
+  struct Params {
+    float scale, alpha, bias;
+    const float* rowterm;  // [batches*M]
+    const float* colterm;  // [batches*N]
+    float* out;            // [batches, M, N]
+  };
+  static constexpr int kSmemBytes = BLOCK_N * 4;
+  const Params& p;
+  const GemmShape& s;
+  float* s_ct;
+  __device__ EpiConfStore(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_) {
+    s_ct = reinterpret_cast<float*>(smem);
+  }
+  __device__ void item_begin(int, int, int) {}
+  __device__ void item_end(int, int, int) {}
+  __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
+    const int t = epi_tid();
+    for (int j = t; j < BLOCK_N; j += kEpiThreads) {
+      const int col = n0 + j;
+      s_ct[j] = (col < s.N) ? p.colterm[static_cast<long>(batch) * s.N + col] : kNegBig;
+    }
+    const int r = m0 + epi_row();
+    const bool row_ok = r < s.M;
+    const float rt = row_ok ? p.rowterm[static_cast<long>(batch) * s.M + r] : kNegBig;
+    const float sa = p.scale * p.alpha;
+    epi_bar_sync();
+    float* orow = p.out + (static_cast<long>(batch) * s.M + r) * s.N;
+    const int c_begin = epi_half() * (BLOCK_N / 64);
+#pragma unroll 1
+    for (int c = c_begin; c < c_begin + BLOCK_N / 64; ++c) {
+      const int col = n0 + c * 32;
+      if (col >= s.N) break;
+      float z[32];
+      load_acc32(tmem_acc, c * 32, z);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float ct = s_ct[c * 32 + j];
+        z[j] = (rt > -1.0e29f && ct > -1.0e29f) ? expf(z[j] * sa + rt + ct + p.bias) : 0.f;
+      }
+      if (row_ok) {
+        if (col + 32 <= s.N && (s.N & 3) == 0) {
+          store_f32x32(orow + col, z);
+        } else {
+          for (int j = 0; j < 32 && col + j < s.N; ++j) orow[col + j] = z[j];
+        }
+      }
+    }
+    epi_bar_sync();
   }
 };
 

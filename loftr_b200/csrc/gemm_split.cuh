@@ -75,7 +75,20 @@ struct GemmSmem {
 //   __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0);   // tmem_acc: column base of this
 //                                                                         // tile's accumulator (lane field 0)
 //   __device__ void item_end(int batch, int m0, int chunk);
-template <int BLOCK_N, class Epi>
+//
+// kDual: the two correction products (hi*lo, lo*hi) accumulate into a SECOND TMEM accumulator that the epilogue adds
+// once.  tcgen05 rounds the fp32 accumulator by truncation at every MMA, so with a single accumulator a K-long
+// contraction suffers 3K/16 biased roundings at full magnitude; with the split only the K/16 hi*hi adds do (the
+// corrections are ~2^-11 of the result, their rounding is negligible).  Used for the long-K convolutions.
+// TMEM columns per stage = BLOCK_N (single) or 2*BLOCK_N (dual); two stages whenever they fit in 512 columns.
+template <int BLOCK_N, bool kDual>
+struct AccLayout {
+  static constexpr int kColsPerStage = kDual ? 2 * BLOCK_N : BLOCK_N;
+  static constexpr int kStages = (2 * kColsPerStage <= 512) ? 2 : 1;
+  static constexpr uint32_t kTmemCols = kStages * kColsPerStage;  // 256 or 512: a power of two
+};
+
+template <int BLOCK_N, class Epi, bool kDual = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -94,7 +107,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // 256 or 512: power of two
+  using AL = AccLayout<BLOCK_N, kDual>;
+  constexpr uint32_t kTmemCols = AL::kTmemCols;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a_hi);
@@ -180,7 +194,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         for (int nt = nt_begin; nt < nt_end; ++nt) {
           mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+          const uint32_t d_tmem = tmem_base + acc * AL::kColsPerStage;
+          const uint32_t d_corr = kDual ? d_tmem + BLOCK_N : d_tmem;
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
@@ -193,9 +208,10 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
               // advance 16 fp16 = 32 bytes along K inside the 128B swizzle row: +2 in 16-byte units
               const uint64_t adv = static_cast<uint64_t>(k * 2);
-              umma_f16(d_tmem, da_hi + adv, db_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
-              umma_f16(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
-              umma_f16(d_tmem, da_lo + adv, db_hi + adv, idesc, 1u);
+              const uint32_t not_first = (kb | k) != 0 ? 1u : 0u;
+              umma_f16(d_tmem, da_hi + adv, db_hi + adv, idesc, not_first);
+              umma_f16(d_corr, da_hi + adv, db_lo + adv, idesc, kDual ? not_first : 1u);
+              umma_f16(d_corr, da_lo + adv, db_hi + adv, idesc, 1u);
             }
             umma_commit(&empty_bar[stage]);
             if (++stage == S::kStages) {
@@ -204,7 +220,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             }
           }
           umma_commit(&tmem_full[acc]);
-          if (++acc == 2) {
+          if (++acc == AL::kStages) {
             acc = 0;
             acc_phase ^= 1;
           }
@@ -226,10 +242,10 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
       for (int nt = nt_begin; nt < nt_end; ++nt) {
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
-        epi.tile(tmem_base + acc * BLOCK_N, batch, mt * kBlockM, nt * BLOCK_N);
+        epi.tile(tmem_base + acc * AL::kColsPerStage, batch, mt * kBlockM, nt * BLOCK_N);
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
-        if (++acc == 2) {
+        if (++acc == AL::kStages) {
           acc = 0;
           acc_phase ^= 1;
         }

@@ -330,6 +330,10 @@ class CoarseMatching(nn.Module):
         a.capacity = cap
         a.b_ids, a.i_ids, a.j_ids = b_ids.data_ptr(), i_ids.data_ptr(), j_ids.data_ptr()
         a.mconf, a.mkpts0_c, a.mkpts1_c, a.count = mconf.data_ptr(), mk0.data_ptr(), mk1.data_ptr(), count.data_ptr()
+        conf = None
+        if self.config.get("return_conf_matrix", False):   # opt-in: 4*L*S bytes per pair, training-loss input only
+            conf = torch.empty(n, L, S, dtype=torch.float32, device=dev)
+            a.conf_matrix = conf.data_ptr()
         nbytes = lib.lb_coarse_match_workspace_bytes(n, L, S)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         _lib.check(lib.lb_coarse_match(C.byref(a), ws.data_ptr(), nbytes, _stream()))
@@ -338,6 +342,8 @@ class CoarseMatching(nn.Module):
             raise RuntimeError(f"loftr_b200: {m} coarse matches exceed the buffer capacity {cap}")
         b_ids, i_ids, j_ids, mconf, mk0, mk1 = b_ids[:m], i_ids[:m], j_ids[:m], mconf[:m], mk0[:m], mk1[:m]
         data.update({"b_ids": b_ids, "i_ids": i_ids, "j_ids": j_ids})
+        if conf is not None:
+            data["conf_matrix"] = conf
         if self.thr >= 0:  # conf > thr >= 0  =>  the reference's `mconf != 0` filter keeps everything
             data.update({"gt_mask": torch.zeros(m, dtype=torch.bool, device=dev), "m_bids": b_ids,
                          "mkpts0_c": mk0, "mkpts1_c": mk1, "mconf": mconf})

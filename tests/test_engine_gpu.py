@@ -84,6 +84,7 @@ def test_coarse_matching_matches_reference_golden(case):
     import loftr_b200.loftr as L
     gold = util.load_golden(case["name"])
     cfg = build_cfg(case)["match_coarse"]
+    cfg["return_conf_matrix"] = True
     inp = build_cm_inputs(case)
     mod = L.CoarseMatching(cfg).eval().to(DEV)
     if cfg["match_type"] == "sinkhorn":
@@ -99,6 +100,14 @@ def test_coarse_matching_matches_reference_golden(case):
     stats = util.compare_matches(got, gold, gold, conf_rtol=1e-3, px_tol=1e-3, min_overlap=1.0, label=case["name"])
     assert stats["n"] == len(gold["b_ids"])
     assert data["b_ids"].dtype == torch.int64 and data["mconf"].dtype == torch.float32
+    # opt-in conf_matrix: identical to the reference's except on cells where both the row and the column are
+    # padding (reference: 1/(L*S)-like constants, engine: 0 -- documented deviation, never matchable)
+    conf = data["conf_matrix"].cpu().numpy()
+    ref = gold["conf_matrix"]
+    if "mask0" in inp:
+        valid = inp["mask0"].reshape(ref.shape[0], -1)[:, :, None] | inp["mask1"].reshape(ref.shape[0], -1)[:, None, :]
+        conf, ref = conf * valid, ref * valid
+    np.testing.assert_allclose(conf, ref, rtol=2e-3, atol=1e-9)
 
 
 def test_coarse_matching_full_size_vs_oracle():
