@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -168,6 +169,68 @@ struct Planes {
 };
 
 // ------------------------------------------------------------------------------------------------ GEMM launch
+// Thread-block-cluster size used by the tensor-core kernels (see gemm_split.cuh, kCluster).  Measured on B200
+// (profiles/r1_cluster_multicast_ab.md): pairing CTAs and TMA-multicasting the B tile is bit-identical but NOT
+// faster -- L2 already de-duplicates concurrent reads of a line, and the binding limit is the per-SM ingest of
+// ~43 B/clk, which multicast does not reduce.  The single-CTA kernels therefore stay the default;
+// LOFTR_B200_CLUSTER=2 selects the multicast pair kernels (kept: they are the scaffolding for cta_group::2).
+static int cluster_size() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LOFTR_B200_CLUSTER");
+    v = (e && atoi(e) == 2) ? 2 : 1;
+  }
+  return v;
+}
+
+template <int BN, class Epi, bool kDual, int kCluster>
+static int launch_raw(int tag, const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
+                      const CUtensorMap& mb_lo, const GemmShape& s, const typename Epi::Params& ep, int sms,
+                      cudaStream_t st) {
+  using S = GemmSmem<BN>;
+  constexpr int smem_bytes = S::kRingBytes + S::kBarBytes + Epi::kSmemBytes + 1024;
+  static_assert(smem_bytes <= 232448, "shared memory budget exceeded");
+  auto kern = gemm_split_kernel<BN, Epi, kDual, kCluster>;
+  static bool configured[kMaxDevices] = {false};  // per instantiation and device
+  int dev = 0;
+  LB_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev]) {
+    LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured[dev] = true;
+  }
+  const long m_groups = (s.m_tiles + kCluster - 1) / kCluster;
+  const long items = static_cast<long>(s.batches) * m_groups * s.n_chunks;
+  const long max_groups = sms / kCluster;
+  const int grid = static_cast<int>((items < max_groups ? items : max_groups) * kCluster);
+  TimingRec rec{nullptr, nullptr, tag};
+  if (g_timing) {
+    LB_CUDA(cudaEventCreate(&rec.e0));
+    LB_CUDA(cudaEventCreate(&rec.e1));
+    LB_CUDA(cudaEventRecord(rec.e0, st));
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, s, ep));
+  LB_LAUNCHED();
+  if (g_timing) {
+    LB_CUDA(cudaEventRecord(rec.e1, st));
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    g_recs.push_back(rec);
+  }
+  return 0;
+}
+
 template <int BN, class Epi>
 static int launch_gemm(int tag, const Planes& A, const Planes& B, int batches, int M, int N, int K, int n_chunks,
                        const typename Epi::Params& ep, cudaStream_t st) {
@@ -188,40 +251,15 @@ static int launch_gemm(int tag, const Planes& A, const Planes& B, int batches, i
   s.n_chunks = (s.n_tiles + s.tiles_per_chunk - 1) / s.tiles_per_chunk;
   s.conv = ConvGeom{0, 0, 0, 0, 0, 0};
 
+  const int cl = (cluster_size() == 2 && s.m_tiles >= 2) ? 2 : 1;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   LB_TRY(make_map(&ma_hi, A.hi, K, M, batches, A.ld, A.batch_stride, kBlockM));
   LB_TRY(make_map(&ma_lo, A.lo, K, M, batches, A.ld, A.batch_stride, kBlockM));
   const int bb = s.b_batched ? batches : 1;
-  LB_TRY(make_map(&mb_hi, B.hi, K, N, bb, B.ld, B.batch_stride, BN));
-  LB_TRY(make_map(&mb_lo, B.lo, K, N, bb, B.ld, B.batch_stride, BN));
-
-  using S = GemmSmem<BN>;
-  constexpr int smem_bytes = S::kRingBytes + S::kBarBytes + Epi::kSmemBytes + 1024;
-  static_assert(smem_bytes <= 232448, "shared memory budget exceeded");
-  auto kern = gemm_split_kernel<BN, Epi>;
-  static bool configured[kMaxDevices] = {false};  // per instantiation and device
-  int dev = 0;
-  LB_CUDA(cudaGetDevice(&dev));
-  if (!configured[dev]) {
-    LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured[dev] = true;
-  }
-  const long items = static_cast<long>(batches) * s.m_tiles * s.n_chunks;
-  const int grid = static_cast<int>(items < sms ? items : sms);
-  TimingRec rec{nullptr, nullptr, tag};
-  if (g_timing) {
-    LB_CUDA(cudaEventCreate(&rec.e0));
-    LB_CUDA(cudaEventCreate(&rec.e1));
-    LB_CUDA(cudaEventRecord(rec.e0, st));
-  }
-  kern<<<grid, kGemmThreads, smem_bytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, s, ep);
-  LB_LAUNCHED();
-  if (g_timing) {
-    LB_CUDA(cudaEventRecord(rec.e1, st));
-    std::lock_guard<std::mutex> lk(g_timing_mu);
-    g_recs.push_back(rec);
-  }
-  return 0;
+  LB_TRY(make_map(&mb_hi, B.hi, K, N, bb, B.ld, B.batch_stride, BN / cl));
+  LB_TRY(make_map(&mb_lo, B.lo, K, N, bb, B.ld, B.batch_stride, BN / cl));
+  if (cl == 2) return launch_raw<BN, Epi, false, 2>(tag, ma_hi, ma_lo, mb_hi, mb_lo, s, ep, sms, st);
+  return launch_raw<BN, Epi, false, 1>(tag, ma_hi, ma_lo, mb_hi, mb_lo, s, ep, sms, st);
 }
 
 // Implicit-GEMM convolution launch: in = NHWC planes [N, H_in, W_in, ld_in] with Cin valid channels; weights =
@@ -249,42 +287,19 @@ static int launch_conv(const Planes& in, const Planes& wgt, const ConvDesc& d, c
   s.n_chunks = s.n_tiles;
   s.tiles_per_chunk = 1;
   s.conv = ConvGeom{1, tiles_w, d.stride, d.pad, d.ksize, cin_blocks};
+  const int cl = (cluster_size() == 2 && s.m_tiles >= 2) ? 2 : 1;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   LB_TRY(make_map_nhwc(&ma_hi, in.hi, d.Cin, d.W_in, d.H_in, d.N, in.ld, d.stride));
   LB_TRY(make_map_nhwc(&ma_lo, in.lo, d.Cin, d.W_in, d.H_in, d.N, in.ld, d.stride));
-  LB_TRY(make_map(&mb_hi, wgt.hi, s.K, d.Cout, 1, wgt.ld, 0, BN));
-  LB_TRY(make_map(&mb_lo, wgt.lo, s.K, d.Cout, 1, wgt.ld, 0, BN));
+  LB_TRY(make_map(&mb_hi, wgt.hi, s.K, d.Cout, 1, wgt.ld, 0, BN / cl));
+  LB_TRY(make_map(&mb_lo, wgt.lo, s.K, d.Cout, 1, wgt.ld, 0, BN / cl));
   typename Epi::Params ep = ep_in;
   ep.H_out = d.H_out;
   ep.W_out = d.W_out;
   ep.tiles_w = tiles_w;
-  using S = GemmSmem<BN>;
-  constexpr int smem_bytes = S::kRingBytes + S::kBarBytes + Epi::kSmemBytes + 1024;
-  static_assert(smem_bytes <= 232448, "shared memory budget exceeded");
-  auto kern = gemm_split_kernel<BN, Epi, true>;   // dual accumulator: EpiConv adds the correction accumulator
-  static bool configured[kMaxDevices] = {false};
-  int dev = 0;
-  LB_CUDA(cudaGetDevice(&dev));
-  if (!configured[dev]) {
-    LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured[dev] = true;
-  }
-  const long items = static_cast<long>(s.batches) * s.m_tiles * s.n_chunks;
-  const int grid = static_cast<int>(items < sms ? items : sms);
-  TimingRec rec{nullptr, nullptr, TAG_CONV};
-  if (g_timing) {
-    LB_CUDA(cudaEventCreate(&rec.e0));
-    LB_CUDA(cudaEventCreate(&rec.e1));
-    LB_CUDA(cudaEventRecord(rec.e0, st));
-  }
-  kern<<<grid, kGemmThreads, smem_bytes, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, s, ep);
-  LB_LAUNCHED();
-  if (g_timing) {
-    LB_CUDA(cudaEventRecord(rec.e1, st));
-    std::lock_guard<std::mutex> lk(g_timing_mu);
-    g_recs.push_back(rec);
-  }
-  return 0;
+  // dual accumulator: EpiConv adds the correction accumulator
+  if (cl == 2) return launch_raw<BN, Epi, true, 2>(TAG_CONV, ma_hi, ma_lo, mb_hi, mb_lo, s, ep, sms, st);
+  return launch_raw<BN, Epi, true, 1>(TAG_CONV, ma_hi, ma_lo, mb_hi, mb_lo, s, ep, sms, st);
 }
 
 // number of n-chunks that gives every SM a few work items when a CTA must sweep many n tiles

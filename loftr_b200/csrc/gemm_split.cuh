@@ -88,7 +88,14 @@ struct AccLayout {
   static constexpr uint32_t kTmemCols = kStages * kColsPerStage;  // 256 or 512: a power of two
 };
 
-template <int BLOCK_N, class Epi, bool kDual = false>
+//
+// kCluster = 2: thread-block clusters of two CTAs that work on two adjacent row tiles of the SAME column tile.
+// Each CTA fetches half of the B tile and TMA-multicasts it into both CTAs' shared memory, so the L2 -> SM
+// traffic per MMA drops from (A + B) to (A + B/2) bytes -- the single-CTA kernel is bound by exactly that feed
+// (measured 42.8 B/clk/SM = the ~6.3 KB/clk L2 output limit, at 45-55 % tensor-pipe utilisation).  A stage may be
+// overwritten only after the MMAs of BOTH CTAs have read it: the empty barriers count two arrivals and every MMA
+// warp commits to the barrier of both CTAs (tcgen05.commit ... multicast::cluster).
+template <int BLOCK_N, class Epi, bool kDual = false, int kCluster = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -119,7 +126,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], kCluster);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -132,21 +139,29 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();   // peer barriers are initialised before anyone multicasts / commits to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_kb = shape.K / kBlockK;
-  const int total_items = shape.batches * shape.m_tiles * shape.n_chunks;
+  // Work items.  Single CTA: (batch, m_tile, chunk).  Cluster: (batch, m_tile group, chunk); CTA rank r of the
+  // cluster takes m_tile = group * kCluster + r (a phantom tile past the end is loaded/multiplied but not emitted).
+  const int crank = kCluster > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int m_groups = (shape.m_tiles + kCluster - 1) / kCluster;
+  const int total_items = shape.batches * m_groups * shape.n_chunks;
+  const int first_item = blockIdx.x / kCluster;
+  const int item_step = gridDim.x / kCluster;
+  constexpr uint16_t kMcMask = static_cast<uint16_t>((1u << kCluster) - 1);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      for (int item = first_item; item < total_items; item += item_step) {
         const int chunk = item % shape.n_chunks;
-        const int mt = (item / shape.n_chunks) % shape.m_tiles;
-        const int batch = item / (shape.n_chunks * shape.m_tiles);
+        const int mt = ((item / shape.n_chunks) % m_groups) * kCluster + crank;
+        const int batch = item / (shape.n_chunks * m_groups);
         const int nt_begin = chunk * shape.tiles_per_chunk;
         const int nt_end = min(nt_begin + shape.tiles_per_chunk, shape.n_tiles);
         for (int nt = nt_begin; nt < nt_end; ++nt) {
@@ -168,9 +183,19 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
               tma_load_3d(st + S::kATile, &tm_a_lo, &full_bar[stage], kb * kBlockK, mt * kBlockM, batch);
             }
             const int bb = shape.b_batched ? batch : 0;
-            tma_load_3d(st + 2 * S::kATile, &tm_b_hi, &full_bar[stage], kb * kBlockK, nt * BLOCK_N, bb);
-            tma_load_3d(st + 2 * S::kATile + S::kBTile, &tm_b_lo, &full_bar[stage], kb * kBlockK,
-                        nt * BLOCK_N, bb);
+            if (kCluster == 1) {
+              tma_load_3d(st + 2 * S::kATile, &tm_b_hi, &full_bar[stage], kb * kBlockK, nt * BLOCK_N, bb);
+              tma_load_3d(st + 2 * S::kATile + S::kBTile, &tm_b_lo, &full_bar[stage], kb * kBlockK,
+                          nt * BLOCK_N, bb);
+            } else {
+              // this CTA's slice of the B tile (BLOCK_N / kCluster rows), delivered to every CTA of the cluster
+              constexpr int kSliceRows = BLOCK_N / kCluster;
+              constexpr int kSliceBytes = S::kBTile / kCluster;
+              tma_load_3d_mc(st + 2 * S::kATile + crank * kSliceBytes, &tm_b_hi, &full_bar[stage], kb * kBlockK,
+                             nt * BLOCK_N + crank * kSliceRows, bb, kMcMask);
+              tma_load_3d_mc(st + 2 * S::kATile + S::kBTile + crank * kSliceBytes, &tm_b_lo, &full_bar[stage],
+                             kb * kBlockK, nt * BLOCK_N + crank * kSliceRows, bb, kMcMask);
+            }
             if (++stage == S::kStages) {
               stage = 0;
               phase ^= 1;
@@ -187,7 +212,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      for (int item = first_item; item < total_items; item += item_step) {
         const int chunk = item % shape.n_chunks;
         const int nt_begin = chunk * shape.tiles_per_chunk;
         const int nt_end = min(nt_begin + shape.tiles_per_chunk, shape.n_tiles);
@@ -213,7 +238,11 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
               umma_f16(d_corr, da_hi + adv, db_lo + adv, idesc, kDual ? not_first : 1u);
               umma_f16(d_corr, da_lo + adv, db_hi + adv, idesc, 1u);
             }
-            umma_commit(&empty_bar[stage]);
+            if (kCluster == 1) {
+              umma_commit(&empty_bar[stage]);
+            } else {
+              umma_commit_mc(&empty_bar[stage], kMcMask);   // frees the slot in every CTA that multicasts into it
+            }
             if (++stage == S::kStages) {
               stage = 0;
               phase ^= 1;
@@ -232,17 +261,18 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
     Epi epi(epi_params, epi_smem, shape);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+    for (int item = first_item; item < total_items; item += item_step) {
       const int chunk = item % shape.n_chunks;
-      const int mt = (item / shape.n_chunks) % shape.m_tiles;
-      const int batch = item / (shape.n_chunks * shape.m_tiles);
+      const int mt = ((item / shape.n_chunks) % m_groups) * kCluster + crank;
+      const int batch = item / (shape.n_chunks * m_groups);
       const int nt_begin = chunk * shape.tiles_per_chunk;
       const int nt_end = min(nt_begin + shape.tiles_per_chunk, shape.n_tiles);
-      epi.item_begin(batch, mt * kBlockM, chunk);
+      const bool real = mt < shape.m_tiles;   // phantom row tile of an odd tail: consume, emit nothing
+      if (real) epi.item_begin(batch, mt * kBlockM, chunk);
       for (int nt = nt_begin; nt < nt_end; ++nt) {
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
-        epi.tile(tmem_base + acc * AL::kColsPerStage, batch, mt * kBlockM, nt * BLOCK_N);
+        if (real) epi.tile(tmem_base + acc * AL::kColsPerStage, batch, mt * kBlockM, nt * BLOCK_N);
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
         if (++acc == AL::kStages) {
@@ -250,12 +280,13 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
           acc_phase ^= 1;
         }
       }
-      epi.item_end(batch, mt * kBlockM, chunk);
+      if (real) epi.item_end(batch, mt * kBlockM, chunk);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();   // no CTA may exit while its peer can still signal its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
