@@ -553,6 +553,11 @@ struct EpiScoreLse {
     epi_bar_sync();
 
     const int c_begin = epi_half() * (BLOCK_N / 64);
+    // Fast path (dual-softmax without padding masks): rows and columns share ONE exponential per element,
+    // e = exp(z - g) with g the maximum of the warp's 32 x 32 block; a (g, sum) pair is a valid partial for both
+    // directions.  If any row or column of the block sits more than ~69 nats below g (its sum would lose
+    // significant terms to fp32 underflow) the whole block falls back to the per-row / per-column references.
+    const bool shared_ref = kRows && kCols && p.colterm == nullptr && p.rowterm == nullptr;
 #pragma unroll 1
     for (int c = c_begin; c < c_begin + BLOCK_N / 64; ++c) {
       if (n0 + c * 32 >= s.N) break;
@@ -560,6 +565,34 @@ struct EpiScoreLse {
       load_acc32(tmem_acc, c * 32, z);
 #pragma unroll
       for (int j = 0; j < 32; ++j) z[j] *= p.scale;
+
+      if (kRows && kCols && shared_ref && n0 + c * 32 + 32 <= s.N) {   // warp-uniform condition
+        const bool row_valid = r < s.M;
+        float cm = kNegBig;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) cm = fmaxf(cm, z[j]);
+        if (!row_valid) cm = kNegBig;
+        float g = cm;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, o));
+        float v[32];
+        float rs = 0.f;
+        const float gl = g * kLog2e;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = row_valid ? ex2_approx(fmaf(z[j], kLog2e, -gl)) : 0.f;
+          rs += v[j];
+        }
+        const float csum = warp_transpose_reduce(v, OpAddF());   // lane j: sum over the block's rows of column j
+        const bool fine = (rs >= 1e-30f || !row_valid) && (csum >= 1e-30f);
+        if (__all_sync(0xffffffffu, fine)) {
+          const float m_new = fmaxf(row_m, g);
+          row_l = row_l * exp_fast(row_m - m_new) + rs * exp_fast(g - m_new);
+          row_m = m_new;
+          s_cpart[q * BLOCK_N + c * 32 + lane] = make_float2(g, csum);
+          continue;
+        }
+      }
 
       if (kRows) {
         float cm = kNegBig;

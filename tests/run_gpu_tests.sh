@@ -9,6 +9,7 @@ groups=(
   "tests/test_engine_gpu.py::test_transformer_matches_oracle"
   "tests/test_engine_gpu.py::test_coarse_matching_matches_reference_golden"
   "tests/test_engine_gpu.py::test_coarse_matching_full_size_vs_oracle"
+  "tests/test_engine_gpu.py::test_coarse_matching_large_logit_spread"
   "tests/test_engine_gpu.py::test_fine_level_matches_oracle"
   "tests/test_engine_gpu.py::test_end_to_end_matches_reference_golden"
   "tests/test_engine_gpu.py::test_end_to_end_640x480_vs_oracle"

@@ -339,3 +339,29 @@ def test_tensor_core_backbone_matches_torch(shape):
         # the bias compounds over the ~20 convolutions.  It stays well inside what the matcher tolerances need
         # (end-to-end mconf rel err 5e-4 < 1e-3, see parity_stats); bound it so regressions are caught.
         assert err_ours <= 1e-4 * scale, f"{name}: {err_ours:.3e} (torch fp32: {err_torch:.3e}, scale {scale:.3e})"
+
+
+def test_coarse_matching_large_logit_spread():
+    """Logits spanning hundreds of nats inside one 32x32 block: the shared-reference fast path of the LSE
+    epilogue must detect the underflow risk and fall back to per-row / per-column references."""
+    import loftr_b200.loftr as L
+    rs = np.random.RandomState(21)
+    n, h, w, c = 2, 20, 24, 256
+    f0 = (rs.standard_normal((n, h * w, c)) * 3.0).astype(np.float32)
+    f1 = (rs.standard_normal((n, h * w, c)) * 3.0).astype(np.float32)
+    k = 200
+    for b in range(n):
+        src, dst = rs.permutation(h * w)[:k], rs.permutation(h * w)[:k]
+        f1[b, dst] = f0[b, src] * rs.uniform(0.2, 1.5, (k, 1)).astype(np.float32)   # matched logits 18 .. 135
+    f0[:, ::7] *= 0.02                                                                # some nearly featureless rows
+    cfg = build_cfg({"thr": 0.2})["match_coarse"]
+    out = O.coarse_matching(f0, f1, cfg, (h * 8, w * 8), (h, w), (h, w))
+    sim = (f0[0] / 16) @ (f1[0] / 16).T / 0.1
+    assert sim.max() - sim.min() > 150, "the case is meant to have a huge logit spread"
+    mod = L.CoarseMatching(cfg).eval()
+    data = {"hw0_i": (h * 8, w * 8), "hw1_i": (h * 8, w * 8), "hw0_c": (h, w), "hw1_c": (h, w)}
+    mod(_t(f0), _t(f1), data)
+    got = {kk: data[kk].cpu().numpy() for kk in ["b_ids", "i_ids", "j_ids", "mconf", "mkpts0_c", "mkpts1_c"]}
+    assert len(out["b_ids"]) > 50
+    stats = util.compare_matches(got, out, None, conf_rtol=1e-3, px_tol=1e-3, min_overlap=1.0, label="spread")
+    util.record("cm_large_logit_spread", stats)
