@@ -169,28 +169,31 @@ struct Planes {
 };
 
 // ------------------------------------------------------------------------------------------------ GEMM launch
-// Thread-block-cluster size used by the tensor-core kernels (see gemm_split.cuh, kCluster).  Measured on B200
-// (profiles/r1_cluster_multicast_ab.md): pairing CTAs and TMA-multicasting the B tile is bit-identical but NOT
-// faster -- L2 already de-duplicates concurrent reads of a line, and the binding limit is the per-SM ingest of
-// ~43 B/clk, which multicast does not reduce.  The single-CTA kernels therefore stay the default;
-// LOFTR_B200_CLUSTER=2 selects the multicast pair kernels (kept: they are the scaffolding for cta_group::2).
-static int cluster_size() {
+// Execution mode of the tensor-core kernels (gemm_split.cuh kMode): 0 = single CTA, 1 = cluster of two with TMA
+// multicast of the B tile (bit-identical, measured not faster: profiles/r1_cluster_multicast_ab.md), 2 = CTA pairs
+// with tcgen05.mma.cta_group::2.  Selected with LOFTR_B200_MODE.
+#ifndef LB_DEFAULT_MODE
+#define LB_DEFAULT_MODE 0
+#endif
+static int kernel_mode() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("LOFTR_B200_CLUSTER");
-    v = (e && atoi(e) == 2) ? 2 : 1;
+    const char* e = getenv("LOFTR_B200_MODE");
+    v = e ? atoi(e) : LB_DEFAULT_MODE;
+    if (v < 0 || v > 2) v = LB_DEFAULT_MODE;
   }
   return v;
 }
 
-template <int BN, class Epi, bool kDual, int kCluster>
+template <int BN, class Epi, bool kDual, int kMode>
 static int launch_raw(int tag, const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
                       const CUtensorMap& mb_lo, const GemmShape& s, const typename Epi::Params& ep, int sms,
                       cudaStream_t st) {
-  using S = GemmSmem<BN>;
+  constexpr int kCluster = kMode == 0 ? 1 : 2;
+  using S = GemmSmem<BN, kMode == 2>;
   constexpr int smem_bytes = S::kRingBytes + S::kBarBytes + Epi::kSmemBytes + 1024;
   static_assert(smem_bytes <= 232448, "shared memory budget exceeded");
-  auto kern = gemm_split_kernel<BN, Epi, kDual, kCluster>;
+  auto kern = gemm_split_kernel<BN, Epi, kDual, kMode>;
   static bool configured[kMaxDevices] = {false};  // per instantiation and device
   int dev = 0;
   LB_CUDA(cudaGetDevice(&dev));
@@ -251,15 +254,17 @@ static int launch_gemm(int tag, const Planes& A, const Planes& B, int batches, i
   s.n_chunks = (s.n_tiles + s.tiles_per_chunk - 1) / s.tiles_per_chunk;
   s.conv = ConvGeom{0, 0, 0, 0, 0, 0};
 
-  const int cl = (cluster_size() == 2 && s.m_tiles >= 2) ? 2 : 1;
+  const int mode = s.m_tiles >= 2 ? kernel_mode() : 0;
+  const int cl = mode == 0 ? 1 : 2;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   LB_TRY(make_map(&ma_hi, A.hi, K, M, batches, A.ld, A.batch_stride, kBlockM));
   LB_TRY(make_map(&ma_lo, A.lo, K, M, batches, A.ld, A.batch_stride, kBlockM));
   const int bb = s.b_batched ? batches : 1;
   LB_TRY(make_map(&mb_hi, B.hi, K, N, bb, B.ld, B.batch_stride, BN / cl));
   LB_TRY(make_map(&mb_lo, B.lo, K, N, bb, B.ld, B.batch_stride, BN / cl));
-  if (cl == 2) return launch_raw<BN, Epi, false, 2>(tag, ma_hi, ma_lo, mb_hi, mb_lo, s, ep, sms, st);
-  return launch_raw<BN, Epi, false, 1>(tag, ma_hi, ma_lo, mb_hi, mb_lo, s, ep, sms, st);
+  if (mode == 2) return launch_raw<BN, Epi, false, 2>(tag, ma_hi, ma_lo, mb_hi, mb_lo, s, ep, sms, st);
+  if (mode == 1) return launch_raw<BN, Epi, false, 1>(tag, ma_hi, ma_lo, mb_hi, mb_lo, s, ep, sms, st);
+  return launch_raw<BN, Epi, false, 0>(tag, ma_hi, ma_lo, mb_hi, mb_lo, s, ep, sms, st);
 }
 
 // Implicit-GEMM convolution launch: in = NHWC planes [N, H_in, W_in, ld_in] with Cin valid channels; weights =
@@ -287,7 +292,8 @@ static int launch_conv(const Planes& in, const Planes& wgt, const ConvDesc& d, c
   s.n_chunks = s.n_tiles;
   s.tiles_per_chunk = 1;
   s.conv = ConvGeom{1, tiles_w, d.stride, d.pad, d.ksize, cin_blocks};
-  const int cl = (cluster_size() == 2 && s.m_tiles >= 2) ? 2 : 1;
+  const int mode = s.m_tiles >= 2 ? kernel_mode() : 0;
+  const int cl = mode == 0 ? 1 : 2;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   LB_TRY(make_map_nhwc(&ma_hi, in.hi, d.Cin, d.W_in, d.H_in, d.N, in.ld, d.stride));
   LB_TRY(make_map_nhwc(&ma_lo, in.lo, d.Cin, d.W_in, d.H_in, d.N, in.ld, d.stride));
@@ -298,8 +304,9 @@ static int launch_conv(const Planes& in, const Planes& wgt, const ConvDesc& d, c
   ep.W_out = d.W_out;
   ep.tiles_w = tiles_w;
   // dual accumulator: EpiConv adds the correction accumulator
-  if (cl == 2) return launch_raw<BN, Epi, true, 2>(TAG_CONV, ma_hi, ma_lo, mb_hi, mb_lo, s, ep, sms, st);
-  return launch_raw<BN, Epi, true, 1>(TAG_CONV, ma_hi, ma_lo, mb_hi, mb_lo, s, ep, sms, st);
+  if (mode == 2) return launch_raw<BN, Epi, true, 2>(TAG_CONV, ma_hi, ma_lo, mb_hi, mb_lo, s, ep, sms, st);
+  if (mode == 1) return launch_raw<BN, Epi, true, 1>(TAG_CONV, ma_hi, ma_lo, mb_hi, mb_lo, s, ep, sms, st);
+  return launch_raw<BN, Epi, true, 0>(TAG_CONV, ma_hi, ma_lo, mb_hi, mb_lo, s, ep, sms, st);
 }
 
 // number of n-chunks that gives every SM a few work items when a CTA must sweep many n tiles

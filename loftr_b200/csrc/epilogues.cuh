@@ -21,7 +21,7 @@ __device__ __forceinline__ float exp_fast(float x) { return ex2_approx(x * kLog2
 __device__ __forceinline__ int epi_tid() { return threadIdx.x - kEpiWarp0 * 32; }   // 0..255
 __device__ __forceinline__ int epi_row() { return epi_tid() & 127; }                  // accumulator row (TMEM lane)
 __device__ __forceinline__ int epi_half() { return epi_tid() >> 7; }                  // column half of the tile
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { epi_group_sync(); }
 
 // x = hi + lo with both halves fp16 (round-to-nearest); |x| must stay below 65504.
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {

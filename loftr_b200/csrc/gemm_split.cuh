@@ -29,6 +29,8 @@ constexpr int kUmmaK = 16;
 constexpr int kGemmThreads = 384;
 constexpr int kEpiThreads = 256;  // two epilogue warpgroups: rows x {left, right} half of the tile's columns
 constexpr int kEpiWarp0 = 4;
+// named barrier 1 over the 256 epilogue threads (also used by the epilogues themselves)
+__device__ __forceinline__ void epi_group_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // Implicit-GEMM convolution mode: the A operand is an NHWC activation (fp16 planes) read through a 4-D tensor
 // map; a 128-row tile is an 8 x 16 patch of output pixels and k-block kb = (tap, 64-channel block) is the same
@@ -57,16 +59,40 @@ struct GemmShape {
   ConvGeom conv;
 };
 
-template <int BLOCK_N>
+// Shared-memory ring.  kPair (cta_group::2): a CTA stages its own 128 rows of A and only its HALF of the B tile.
+template <int BLOCK_N, bool kPair = false>
 struct GemmSmem {
-  static constexpr int kATile = kBlockM * kBlockK * 2;      // 16 KB
-  static constexpr int kBTile = BLOCK_N * kBlockK * 2;      // 16/32 KB
-  static constexpr int kStageBytes = 2 * kATile + 2 * kBTile;
-  static constexpr int kStages = (BLOCK_N == 256) ? 2 : 3;
-  static constexpr int kRingBytes = kStages * kStageBytes;  // 192 KB
+  static constexpr int kATile = kBlockM * kBlockK * 2;                       // 16 KB per plane
+  static constexpr int kBTile = (kPair ? BLOCK_N / 2 : BLOCK_N) * kBlockK * 2;  // per plane
+  static constexpr int kStageBytes = 2 * kATile + 2 * kBTile;                // hi + lo of A and B
+  static constexpr int kStages = (192 * 1024) / kStageBytes;                 // 2 (96 KB) / 3 (64 KB) / 4 (48 KB)
+  static constexpr int kRingBytes = kStages * kStageBytes;
   static constexpr int kBarBytes = 256;
 };
 
+// TMEM layout.  kDual: the two correction products (hi*lo, lo*hi) accumulate into a SECOND accumulator that the
+// epilogue adds once.  tcgen05 rounds the fp32 accumulator by truncation at every MMA, so with a single accumulator
+// a K-long contraction suffers 3K/16 biased roundings at full magnitude; with the split only the K/16 hi*hi adds do
+// (the corrections are ~2^-11 of the result, their rounding is negligible).  Used for the long-K convolutions.
+// Columns per stage = BLOCK_N (single) or 2*BLOCK_N (dual); two stages whenever they fit in 512 columns.
+template <int BLOCK_N, bool kDual>
+struct AccLayout {
+  static constexpr int kColsPerStage = kDual ? 2 * BLOCK_N : BLOCK_N;
+  static constexpr int kStages = (2 * kColsPerStage <= 512) ? 2 : 1;
+  static constexpr uint32_t kTmemCols = kStages * kColsPerStage;  // 256 or 512: a power of two
+};
+
+// Execution modes (kMode):
+//   0  single CTA per tile (cta_group::1).
+//   1  cluster of two CTAs on adjacent row tiles; each fetches half of the B tile and TMA-multicasts it to both
+//      (cta_group::1 MMAs).  Bit-identical, measured NOT faster: the kernels are bound by bytes delivered per SM.
+//   2  CTA pair with tcgen05.mma.cta_group::2: the leader (even CTA) issues M = 256 MMAs over both CTAs' TMEM; each
+//      CTA stages its own A rows and only HALF of B, so the L2 -> SM bytes per MMA drop from A + B to A + B/2.
+//      Barrier protocol (CUTLASS/DeepGEMM 2-SM scheme): both producers' TMA bytes are credited to the LEADER's full
+//      barrier (count 2: the leader arms expect_tx for both CTAs, the peer arrives remotely); the leader's
+//      tcgen05.commit multicasts to both CTAs' empty / tmem_full barriers; one thread per CTA arrives (remotely for
+//      the peer) on the leader's tmem_empty barrier once its epilogue has drained the accumulator.
+//
 // Epilogue contract (all methods are called by the 256 epilogue threads only):
 //   struct Params;                               // trivially copyable, passed by value to the kernel
 //   static constexpr int kSmemBytes;             // extra dynamic smem the epilogue wants
@@ -75,32 +101,15 @@ struct GemmSmem {
 //   __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0);   // tmem_acc: column base of this
 //                                                                         // tile's accumulator (lane field 0)
 //   __device__ void item_end(int batch, int m0, int chunk);
-//
-// kDual: the two correction products (hi*lo, lo*hi) accumulate into a SECOND TMEM accumulator that the epilogue adds
-// once.  tcgen05 rounds the fp32 accumulator by truncation at every MMA, so with a single accumulator a K-long
-// contraction suffers 3K/16 biased roundings at full magnitude; with the split only the K/16 hi*hi adds do (the
-// corrections are ~2^-11 of the result, their rounding is negligible).  Used for the long-K convolutions.
-// TMEM columns per stage = BLOCK_N (single) or 2*BLOCK_N (dual); two stages whenever they fit in 512 columns.
-template <int BLOCK_N, bool kDual>
-struct AccLayout {
-  static constexpr int kColsPerStage = kDual ? 2 * BLOCK_N : BLOCK_N;
-  static constexpr int kStages = (2 * kColsPerStage <= 512) ? 2 : 1;
-  static constexpr uint32_t kTmemCols = kStages * kColsPerStage;  // 256 or 512: a power of two
-};
-
-//
-// kCluster = 2: thread-block clusters of two CTAs that work on two adjacent row tiles of the SAME column tile.
-// Each CTA fetches half of the B tile and TMA-multicasts it into both CTAs' shared memory, so the L2 -> SM
-// traffic per MMA drops from (A + B) to (A + B/2) bytes -- the single-CTA kernel is bound by exactly that feed
-// (measured 42.8 B/clk/SM = the ~6.3 KB/clk L2 output limit, at 45-55 % tensor-pipe utilisation).  A stage may be
-// overwritten only after the MMAs of BOTH CTAs have read it: the empty barriers count two arrivals and every MMA
-// warp commits to the barrier of both CTAs (tcgen05.commit ... multicast::cluster).
-template <int BLOCK_N, class Epi, bool kDual = false, int kCluster = 1>
+template <int BLOCK_N, class Epi, bool kDual = false, int kMode = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                   const GemmShape shape, const typename Epi::Params epi_params) {
-  using S = GemmSmem<BLOCK_N>;
+  constexpr bool kPair = kMode == 2;
+  constexpr bool kMcast = kMode == 1;
+  constexpr int kCluster = kMode == 0 ? 1 : 2;
+  using S = GemmSmem<BLOCK_N, kPair>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // Dynamic smem base is only guaranteed 16B aligned; the swizzled tiles need 1024B.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -116,6 +125,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   const int lane = threadIdx.x & 31;
   using AL = AccLayout<BLOCK_N, kDual>;
   constexpr uint32_t kTmemCols = AL::kTmemCols;
+  const int crank = kCluster > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const bool leader = crank == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a_hi);
@@ -125,28 +136,31 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S::kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kCluster);
+      mbar_init(&full_bar[s], kPair ? 2 : 1);          // pair: one arrival per CTA's producer (on the leader's copy)
+      mbar_init(&empty_bar[s], kMcast ? 2 : 1);        // multicast mode: both CTAs' MMAs must have read the slot
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], kEpiThreads);
+      mbar_init(&tmem_empty[a], kPair ? 2 : kEpiThreads);  // pair: one elected thread per CTA
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, kTmemCols);
+    if (kPair) {
+      tmem_alloc_2sm(tmem_slot, kTmemCols);
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (kCluster > 1) cluster_sync_all();   // peer barriers are initialised before anyone multicasts / commits to them
+  if (kCluster > 1) cluster_sync_all();   // peer barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_kb = shape.K / kBlockK;
   // Work items.  Single CTA: (batch, m_tile, chunk).  Cluster: (batch, m_tile group, chunk); CTA rank r of the
   // cluster takes m_tile = group * kCluster + r (a phantom tile past the end is loaded/multiplied but not emitted).
-  const int crank = kCluster > 1 ? static_cast<int>(cluster_ctarank()) : 0;
   const int m_groups = (shape.m_tiles + kCluster - 1) / kCluster;
   const int total_items = shape.batches * m_groups * shape.n_chunks;
   const int first_item = blockIdx.x / kCluster;
@@ -168,7 +182,18 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = ring + stage * S::kStageBytes;
-            mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+            uint64_t* fb = &full_bar[stage];
+            if (kPair) {
+              // both CTAs' bytes are credited to the leader's barrier
+              if (leader) {
+                mbar_arrive_expect_tx(fb, 2 * S::kStageBytes);
+              } else {
+                mbar_arrive_remote(fb, 0);
+              }
+            } else {
+              mbar_arrive_expect_tx(fb, S::kStageBytes);
+            }
+            // ---- A: this CTA's 128 rows (or 8 x 16 pixel patch shifted by the tap)
             if (shape.conv.enabled) {
               const ConvGeom& g = shape.conv;
               const int tap = kb / g.cin_blocks, cb = kb - tap * g.cin_blocks;
@@ -176,25 +201,38 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
               const int ty = mt / g.tiles_w, tx = mt - ty * g.tiles_w;
               const int x = tx * kConvTileW * g.stride + kx - g.pad;
               const int y = ty * kConvTileH * g.stride + ky - g.pad;
-              tma_load_4d(st, &tm_a_hi, &full_bar[stage], cb * kBlockK, x, y, batch);
-              tma_load_4d(st + S::kATile, &tm_a_lo, &full_bar[stage], cb * kBlockK, x, y, batch);
+              if (kPair) {
+                tma_load_4d_2sm(st, &tm_a_hi, fb, cb * kBlockK, x, y, batch);
+                tma_load_4d_2sm(st + S::kATile, &tm_a_lo, fb, cb * kBlockK, x, y, batch);
+              } else {
+                tma_load_4d(st, &tm_a_hi, fb, cb * kBlockK, x, y, batch);
+                tma_load_4d(st + S::kATile, &tm_a_lo, fb, cb * kBlockK, x, y, batch);
+              }
+            } else if (kPair) {
+              tma_load_3d_2sm(st, &tm_a_hi, fb, kb * kBlockK, mt * kBlockM, batch);
+              tma_load_3d_2sm(st + S::kATile, &tm_a_lo, fb, kb * kBlockK, mt * kBlockM, batch);
             } else {
-              tma_load_3d(st, &tm_a_hi, &full_bar[stage], kb * kBlockK, mt * kBlockM, batch);
-              tma_load_3d(st + S::kATile, &tm_a_lo, &full_bar[stage], kb * kBlockK, mt * kBlockM, batch);
+              tma_load_3d(st, &tm_a_hi, fb, kb * kBlockK, mt * kBlockM, batch);
+              tma_load_3d(st + S::kATile, &tm_a_lo, fb, kb * kBlockK, mt * kBlockM, batch);
             }
+            // ---- B
             const int bb = shape.b_batched ? batch : 0;
-            if (kCluster == 1) {
-              tma_load_3d(st + 2 * S::kATile, &tm_b_hi, &full_bar[stage], kb * kBlockK, nt * BLOCK_N, bb);
-              tma_load_3d(st + 2 * S::kATile + S::kBTile, &tm_b_lo, &full_bar[stage], kb * kBlockK,
-                          nt * BLOCK_N, bb);
-            } else {
-              // this CTA's slice of the B tile (BLOCK_N / kCluster rows), delivered to every CTA of the cluster
+            uint8_t* sb_hi = st + 2 * S::kATile;
+            uint8_t* sb_lo = sb_hi + S::kBTile;
+            if (kPair) {            // this CTA's half of the tile's rows, into its own shared memory
+              const int row0 = nt * BLOCK_N + crank * (BLOCK_N / 2);
+              tma_load_3d_2sm(sb_hi, &tm_b_hi, fb, kb * kBlockK, row0, bb);
+              tma_load_3d_2sm(sb_lo, &tm_b_lo, fb, kb * kBlockK, row0, bb);
+            } else if (kMcast) {    // this CTA's slice, delivered to every CTA of the cluster
               constexpr int kSliceRows = BLOCK_N / kCluster;
               constexpr int kSliceBytes = S::kBTile / kCluster;
-              tma_load_3d_mc(st + 2 * S::kATile + crank * kSliceBytes, &tm_b_hi, &full_bar[stage], kb * kBlockK,
-                             nt * BLOCK_N + crank * kSliceRows, bb, kMcMask);
-              tma_load_3d_mc(st + 2 * S::kATile + S::kBTile + crank * kSliceBytes, &tm_b_lo, &full_bar[stage],
-                             kb * kBlockK, nt * BLOCK_N + crank * kSliceRows, bb, kMcMask);
+              tma_load_3d_mc(sb_hi + crank * kSliceBytes, &tm_b_hi, fb, kb * kBlockK, nt * BLOCK_N + crank * kSliceRows,
+                             bb, kMcMask);
+              tma_load_3d_mc(sb_lo + crank * kSliceBytes, &tm_b_lo, fb, kb * kBlockK, nt * BLOCK_N + crank * kSliceRows,
+                             bb, kMcMask);
+            } else {
+              tma_load_3d(sb_hi, &tm_b_hi, fb, kb * kBlockK, nt * BLOCK_N, bb);
+              tma_load_3d(sb_lo, &tm_b_lo, fb, kb * kBlockK, nt * BLOCK_N, bb);
             }
             if (++stage == S::kStages) {
               stage = 0;
@@ -205,9 +243,9 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16_f32(kBlockM, BLOCK_N);
+    // ------------------------------------------------------------ MMA issuer (pair mode: the leader CTA only)
+    if (lane == 0 && (!kPair || leader)) {
+      constexpr uint32_t idesc = umma_idesc_f16_f32(kPair ? 2 * kBlockM : kBlockM, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -234,21 +272,33 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
               // advance 16 fp16 = 32 bytes along K inside the 128B swizzle row: +2 in 16-byte units
               const uint64_t adv = static_cast<uint64_t>(k * 2);
               const uint32_t not_first = (kb | k) != 0 ? 1u : 0u;
-              umma_f16(d_tmem, da_hi + adv, db_hi + adv, idesc, not_first);
-              umma_f16(d_corr, da_hi + adv, db_lo + adv, idesc, kDual ? not_first : 1u);
-              umma_f16(d_corr, da_lo + adv, db_hi + adv, idesc, 1u);
+              if (kPair) {
+                umma_f16_2sm(d_tmem, da_hi + adv, db_hi + adv, idesc, not_first);
+                umma_f16_2sm(d_corr, da_hi + adv, db_lo + adv, idesc, kDual ? not_first : 1u);
+                umma_f16_2sm(d_corr, da_lo + adv, db_hi + adv, idesc, 1u);
+              } else {
+                umma_f16(d_tmem, da_hi + adv, db_hi + adv, idesc, not_first);
+                umma_f16(d_corr, da_hi + adv, db_lo + adv, idesc, kDual ? not_first : 1u);
+                umma_f16(d_corr, da_lo + adv, db_hi + adv, idesc, 1u);
+              }
             }
-            if (kCluster == 1) {
-              umma_commit(&empty_bar[stage]);
+            if (kPair) {
+              umma_commit_2sm_mc(&empty_bar[stage], kMcMask);   // frees the slot in both CTAs
+            } else if (kMcast) {
+              umma_commit_mc(&empty_bar[stage], kMcMask);
             } else {
-              umma_commit_mc(&empty_bar[stage], kMcMask);   // frees the slot in every CTA that multicasts into it
+              umma_commit(&empty_bar[stage]);
             }
             if (++stage == S::kStages) {
               stage = 0;
               phase ^= 1;
             }
           }
-          umma_commit(&tmem_full[acc]);
+          if (kPair) {
+            umma_commit_2sm_mc(&tmem_full[acc], kMcMask);       // both CTAs' epilogues own half of the rows
+          } else {
+            umma_commit(&tmem_full[acc]);
+          }
           if (++acc == AL::kStages) {
             acc = 0;
             acc_phase ^= 1;
@@ -274,7 +324,12 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
         tc_fence_after();
         if (real) epi.tile(tmem_base + acc * AL::kColsPerStage, batch, mt * kBlockM, nt * BLOCK_N);
         tc_fence_before();
-        mbar_arrive(&tmem_empty[acc]);
+        if (kPair) {
+          epi_group_sync();                                          // every thread of this CTA has drained TMEM
+          if (threadIdx.x == kEpiWarp0 * 32) mbar_arrive_remote(&tmem_empty[acc], 0);
+        } else {
+          mbar_arrive(&tmem_empty[acc]);
+        }
         if (++acc == AL::kStages) {
           acc = 0;
           acc_phase ^= 1;
@@ -286,10 +341,14 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 
   tc_fence_before();
   __syncthreads();
-  if (kCluster > 1) cluster_sync_all();   // no CTA may exit while its peer can still signal its barriers
+  if (kCluster > 1) cluster_sync_all();   // no CTA may exit (or free TMEM) while its peer can still touch it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (kPair) {
+      tmem_dealloc_2sm(tmem_base, kTmemCols);
+    } else {
+      tmem_dealloc(tmem_base, kTmemCols);
+    }
   }
 }
 
