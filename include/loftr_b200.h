@@ -40,6 +40,8 @@ extern "C" {
 #define LB_LAYER_CROSS 1
 
 int lb_version(void);
+/* k-block (in elements) the library was built with: convolution weight planes pad Cin per tap to a multiple of it */
+int lb_block_k(void);
 const char* lb_last_error(void);
 /* number of kernels this library has launched in this process (for bench.py's gpu_launches) */
 long long lb_launch_count(void);

@@ -10,7 +10,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libloftr_b200.so")
+# LOFTR_B200_LIB selects an alternative build of the same sources (e.g. "k32" -> libloftr_b200_k32.so, the
+# 32-element k-block variant used for A/B measurements)
+_VARIANT = os.environ.get("LOFTR_B200_LIB", "")
+LIB_PATH = os.path.join(_HERE, "lib", f"libloftr_b200{'_' + _VARIANT if _VARIANT else ''}.so")
 
 MATCH_DUAL_SOFTMAX = 0
 MATCH_SINKHORN = 1
@@ -90,6 +93,7 @@ class LbFineMatchArgs(C.Structure):
 # name -> (restype, argtypes); the same list is what tests/test_abi.py checks against the header.
 SIGNATURES = {
     "lb_version": (c_int, []),
+    "lb_block_k": (c_int, []),
     "lb_last_error": (C.c_char_p, []),
     "lb_launch_count": (C.c_longlong, []),
     "lb_timing_enable": (c_int, [c_int]),

@@ -134,7 +134,8 @@ static int make_map(CUtensorMap* m, const void* base, long K, long rows, long ba
   cuuint32_t box[3] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, kBlockK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
   return 0;
@@ -155,7 +156,8 @@ static int make_map_nhwc(CUtensorMap* m, const void* base, int C, int W, int H, 
                        static_cast<cuuint32_t>(kConvTileH * stride), 1};
   cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, kBlockK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (NHWC) failed with CUresult %d", static_cast<int>(r));
   return 0;
@@ -170,19 +172,19 @@ struct Planes {
 
 // ------------------------------------------------------------------------------------------------ GEMM launch
 // Execution mode of the tensor-core kernels (gemm_split.cuh kMode): 0 = single CTA, 1 = cluster of two with TMA
-// multicast of the B tile (bit-identical, measured not faster: profiles/r1_cluster_multicast_ab.md), 2 = CTA pairs
-// with tcgen05.mma.cta_group::2.  Selected with LOFTR_B200_MODE.
-#ifndef LB_DEFAULT_MODE
-#define LB_DEFAULT_MODE 0
-#endif
-static int kernel_mode() {
-  static int v = -1;
-  if (v < 0) {
+// multicast of the B tile, 2 = CTA pairs with tcgen05.mma.cta_group::2.  Default policy from the A/B measurement
+// in profiles/r1_kernel_variants_ab.md: the pair kernels win where the MMA phase dominates (convolutions -7 %,
+// mlp[0] -9 %, fine merge -8 %) and lose a little where the epilogue dominates (projections, score passes), so
+// they are used for exactly those launches.  LOFTR_B200_MODE=0|1|2 forces one mode for every launch.
+static int kernel_mode(int tag) {
+  static int forced = -2;
+  if (forced == -2) {
     const char* e = getenv("LOFTR_B200_MODE");
-    v = e ? atoi(e) : LB_DEFAULT_MODE;
-    if (v < 0 || v > 2) v = LB_DEFAULT_MODE;
+    forced = e ? atoi(e) : -1;
+    if (forced < -1 || forced > 2) forced = -1;
   }
-  return v;
+  if (forced >= 0) return forced;
+  return (tag == TAG_CONV || tag == TAG_MLP1 || tag == TAG_FINE_MERGE) ? 2 : 0;
 }
 
 template <int BN, class Epi, bool kDual, int kMode>
@@ -254,7 +256,7 @@ static int launch_gemm(int tag, const Planes& A, const Planes& B, int batches, i
   s.n_chunks = (s.n_tiles + s.tiles_per_chunk - 1) / s.tiles_per_chunk;
   s.conv = ConvGeom{0, 0, 0, 0, 0, 0};
 
-  const int mode = s.m_tiles >= 2 ? kernel_mode() : 0;
+  const int mode = s.m_tiles >= 2 ? kernel_mode(tag) : 0;
   const int cl = mode == 0 ? 1 : 2;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   LB_TRY(make_map(&ma_hi, A.hi, K, M, batches, A.ld, A.batch_stride, kBlockM));
@@ -292,7 +294,7 @@ static int launch_conv(const Planes& in, const Planes& wgt, const ConvDesc& d, c
   s.n_chunks = s.n_tiles;
   s.tiles_per_chunk = 1;
   s.conv = ConvGeom{1, tiles_w, d.stride, d.pad, d.ksize, cin_blocks};
-  const int mode = s.m_tiles >= 2 ? kernel_mode() : 0;
+  const int mode = s.m_tiles >= 2 ? kernel_mode(TAG_CONV) : 0;
   const int cl = mode == 0 ? 1 : 2;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   LB_TRY(make_map_nhwc(&ma_hi, in.hi, d.Cin, d.W_in, d.H_in, d.N, in.ld, d.stride));
@@ -543,6 +545,7 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
 extern "C" {
 
 int lb_version(void) { return 100; }
+int lb_block_k(void) { return kBlockK; }
 const char* lb_last_error(void) { return g_err; }
 long long lb_launch_count(void) { return g_launches.load(); }
 
@@ -802,7 +805,7 @@ int lb_coarse_match(const LbCoarseMatchArgs* a, void* ws, size_t ws_bytes, void*
     return 0;
   }
   if (L != a->h0c * a->w0c || S != a->h1c * a->w1c) return fail("L/S do not match the coarse grid sizes");
-  if (C % kBlockK != 0) return fail("C=%d must be a multiple of 64", C);
+  if (C % kBlockK != 0) return fail("C=%d must be a multiple of %d", C, kBlockK);
   if ((a->mask0 == nullptr) != (a->mask1 == nullptr)) return fail("mask0 and mask1 must be given together");
   if (!ws) return fail("workspace pointer is null");
   Bump b{static_cast<uint8_t*>(ws), ws_bytes};

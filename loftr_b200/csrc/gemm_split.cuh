@@ -24,7 +24,13 @@
 namespace lb {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;  // 64 fp16 = 128 bytes = one swizzle row
+#ifndef LB_BLOCK_K
+#define LB_BLOCK_K 64
+#endif
+// k-block of one pipeline stage: 64 fp16 = one 128-byte swizzle row, or 32 fp16 = one 64-byte swizzle row (twice
+// as many, half as large stages in the same shared memory -> deeper TMA pipeline)
+constexpr int kBlockK = LB_BLOCK_K;
+static_assert(kBlockK == 64 || kBlockK == 32, "supported k-block sizes");
 constexpr int kUmmaK = 16;
 constexpr int kGemmThreads = 384;
 constexpr int kEpiThreads = 256;  // two epilogue warpgroups: rows x {left, right} half of the tile's columns
@@ -58,6 +64,11 @@ struct GemmShape {
   int tiles_per_chunk;
   ConvGeom conv;
 };
+
+// K-major operand tile descriptor for the configured k-block (128-byte or 64-byte swizzle rows).
+__device__ __forceinline__ uint64_t umma_desc_k(uint32_t smem_addr) {
+  return kBlockK == 64 ? umma_desc_k_sw128(smem_addr) : umma_desc_k_sw64(smem_addr);
+}
 
 // Shared-memory ring.  kPair (cta_group::2): a CTA stages its own 128 rows of A and only its HALF of the B tile.
 template <int BLOCK_N, bool kPair = false>
@@ -263,10 +274,10 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t st = smem_u32(ring + stage * S::kStageBytes);
-            const uint64_t da_hi = umma_desc_k_sw128(st);
-            const uint64_t da_lo = umma_desc_k_sw128(st + S::kATile);
-            const uint64_t db_hi = umma_desc_k_sw128(st + 2 * S::kATile);
-            const uint64_t db_lo = umma_desc_k_sw128(st + 2 * S::kATile + S::kBTile);
+            const uint64_t da_hi = umma_desc_k(st);
+            const uint64_t da_lo = umma_desc_k(st + S::kATile);
+            const uint64_t db_hi = umma_desc_k(st + 2 * S::kATile);
+            const uint64_t db_lo = umma_desc_k(st + 2 * S::kATile + S::kBTile);
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
               // advance 16 fp16 = 32 bytes along K inside the 128B swizzle row: +2 in 16-byte units

@@ -85,7 +85,8 @@ class TensorCoreBackbone:
     def _conv(self, conv, bn, keep):
         w = conv.weight.detach().float()                      # [cout, cin, k, k]
         cout, cin, k, _ = w.shape
-        cb = -(-cin // 64) * 64
+        bk = _lib.load().lb_block_k()
+        cb = -(-cin // bk) * bk
         wp = torch.zeros(cout, k * k, cb, device=w.device)
         wp[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, k * k, cin)   # tap-major, channels padded per tap
         hi, lo, acc_scale = split_weight(wp.reshape(cout, k * k * cb))
