@@ -314,7 +314,7 @@ static int launch_conv(const Planes& in, const Planes& wgt, const ConvDesc& d, c
 // number of n-chunks that gives every SM a few work items when a CTA must sweep many n tiles
 static int pick_chunks(int row_items, int n_tiles, int sms) {
   int c = 1;
-  while (static_cast<long>(row_items) * c < 8L * sms && c < n_tiles) ++c;
+  while (static_cast<long>(row_items) * c < 40L * sms && c < n_tiles) ++c;   // fine-grained items: <3 % tail
   return c;
 }
 
@@ -760,7 +760,7 @@ struct CmWs {
   float* conf;
   int *ext0, *ext1;
 };
-constexpr int kMaxChunks = 8;
+constexpr int kMaxChunks = 32;
 
 static void carve_cm(Bump& b, CmWs& w, int n, int L, int S) {
   const size_t nl = static_cast<size_t>(n) * L, ns = static_cast<size_t>(n) * S;
