@@ -249,6 +249,7 @@ def run_b200(args):
     note("single-process warm-up done")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout = the one JSON line
         dist.init_process_group("nccl", device_id=dev)
         note("process group up")
 
