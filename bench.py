@@ -249,7 +249,11 @@ def run_b200(args):
     note("single-process warm-up done")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout = the one JSON line
+        # NCCL prints its version banner to stdout while the communicator is created; stdout must carry exactly one
+        # JSON line, so fd 1 points at stderr during initialisation and the collective warm-up.
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
         note("process group up")
 
@@ -275,6 +279,10 @@ def run_b200(args):
         step(d_img0, d_img1)
     max_over_ranks(0.0)
     barrier()
+    if world > 1:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     note("collective warm-up done")
 
     # ---- device-resident throughput
