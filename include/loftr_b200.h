@@ -46,6 +46,11 @@ const char* lb_last_error(void);
 /* number of kernels this library has launched in this process (for bench.py's gpu_launches) */
 long long lb_launch_count(void);
 
+/* Device self-test: runs both generations of the CUDA-core kernels that have two (kv_partial, stem convolution) on
+ * identical inputs at production shapes, compares the outputs bit for bit and times them; writes a text report.
+ * Returns non-zero if any pair differs.  Allocates and frees its own device buffers; synchronises. */
+int lb_selftest(char* report /*host*/, int report_len);
+
 /* Optional per-launch CUDA-event timing of the tensor-core kernels (events recorded on the launching
  * stream around each kernel while enabled).  lb_timing_enable(1) clears old records and starts recording,
  * lb_timing_collect synchronises the recorded events and returns per-tag total milliseconds and launch counts

@@ -96,6 +96,7 @@ SIGNATURES = {
     "lb_block_k": (c_int, []),
     "lb_last_error": (C.c_char_p, []),
     "lb_launch_count": (C.c_longlong, []),
+    "lb_selftest": (c_int, [C.c_char_p, c_int]),
     "lb_timing_enable": (c_int, [c_int]),
     "lb_timing_num_tags": (c_int, []),
     "lb_timing_tag_name": (C.c_char_p, [c_int]),

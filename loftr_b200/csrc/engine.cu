@@ -187,6 +187,24 @@ static int kernel_mode(int tag) {
   return (tag == TAG_CONV || tag == TAG_MLP1 || tag == TAG_FINE_MERGE) ? 2 : 0;
 }
 
+// Second-generation CUDA-core kernels (kv_partial_v2, conv_stem7x7_v2).  They produce bit-identical results to the
+// first versions (checked on the device by lb_selftest, which also times both); LOFTR_B200_V2=0|1 overrides.
+#ifndef LB_KV_V2_DEFAULT
+#define LB_KV_V2_DEFAULT 0
+#endif
+#ifndef LB_STEM_V2_DEFAULT
+#define LB_STEM_V2_DEFAULT 0
+#endif
+static bool use_v2(int which /*0 = kv_partial, 1 = stem*/) {
+  static int forced = -2;
+  if (forced == -2) {
+    const char* e = getenv("LOFTR_B200_V2");
+    forced = e ? (atoi(e) != 0 ? 1 : 0) : -1;
+  }
+  if (forced >= 0) return forced == 1;
+  return which == 0 ? (LB_KV_V2_DEFAULT != 0) : (LB_STEM_V2_DEFAULT != 0);
+}
+
 template <int BN, class Epi, bool kDual, int kMode>
 static int launch_raw(int tag, const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
                       const CUtensorMap& mb_lo, const GemmShape& s, const typename Epi::Params& ep, int sms,
@@ -487,8 +505,13 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
   if (D == 32) {
     const int rps = cdiv(cdiv(s_group_rows, kKvSplits), 32) * 32;
     const int splits = cdiv(s_group_rows, rps);
-    kv_partial_kernel<32><<<dim3(n_groups_s, H, splits), 256, 0, stream>>>(w.qkv, 3 * C, C, 2 * C, s_base,
-                                                                             s_group_rows, rps, w.kv_part);
+    if (use_v2(0)) {
+      kv_partial_v2_kernel<32, 8><<<dim3(n_groups_s, splits), 256, 0, stream>>>(w.qkv, 3 * C, C, s_base, s_group_rows,
+                                                                                 rps, w.kv_part);
+    } else {
+      kv_partial_kernel<32><<<dim3(n_groups_s, H, splits), 256, 0, stream>>>(w.qkv, 3 * C, C, 2 * C, s_base,
+                                                                               s_group_rows, rps, w.kv_part);
+    }
     LB_LAUNCHED();
     const long total = static_cast<long>(n_groups_s) * H * per;
     kv_merge_kernel<<<cdiv(total, 256), 256, 0, stream>>>(w.kv_part, splits, per, w.kv, total);
@@ -577,6 +600,129 @@ int lb_timing_collect(double* total_ms, long long* counts, int n) {
     }
   }
   return 0;
+}
+
+// Device self-test of the second-generation CUDA-core kernels: runs both versions on identical pseudo-random
+// inputs at production shapes, compares the outputs bit for bit and times them.  Allocates its own buffers.
+static __global__ void selftest_fill_kernel(float* p, long n, unsigned seed, float lo, float hi) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    unsigned x = static_cast<unsigned>(i) * 747796405u + seed * 2891336453u + 1u;
+    x = ((x >> ((x >> 28) + 4u)) ^ x) * 277803737u;
+    x = (x >> 22) ^ x;
+    p[i] = lo + (hi - lo) * (static_cast<float>(x >> 8) * (1.0f / 16777216.0f));
+  }
+}
+static __global__ void selftest_diff_kernel(const unsigned* a, const unsigned* b, long n, unsigned long long* ndiff) {
+  unsigned long long c = 0;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long>(gridDim.x) * blockDim.x)
+    c += a[i] != b[i];
+  if (c) atomicAdd(ndiff, c);
+}
+
+int lb_selftest(char* report, int report_len) {
+  int sms;
+  LB_TRY(device_check(&sms));
+  auto say = [&](const char* fmt, ...) {
+    const int used = static_cast<int>(strlen(report));
+    if (used >= report_len - 1) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(report + used, report_len - used, fmt, ap);
+    va_end(ap);
+  };
+  if (report_len > 0) report[0] = 0;
+  cudaEvent_t e0, e1;
+  LB_CUDA(cudaEventCreate(&e0));
+  LB_CUDA(cudaEventCreate(&e1));
+  unsigned long long* d_ndiff;
+  LB_CUDA(cudaMalloc(&d_ndiff, 8));
+  auto diff = [&](const void* a, const void* b, long words, unsigned long long* out) -> int {
+    LB_CUDA(cudaMemset(d_ndiff, 0, 8));
+    selftest_diff_kernel<<<1024, 256>>>(static_cast<const unsigned*>(a), static_cast<const unsigned*>(b), words, d_ndiff);
+    LB_CUDA(cudaMemcpy(out, d_ndiff, 8, cudaMemcpyDeviceToHost));
+    return 0;
+  };
+  int failures = 0;
+  {  // ---- kv_partial: 16 images x 4800 tokens, C = 256 (batch 8 at 640x480)
+    const int C = 256, H = 8, D = 32, groups = 16, rows_per_group = 4800;
+    const long R = static_cast<long>(groups) * rows_per_group;
+    const int rps = cdiv(cdiv(rows_per_group, kKvSplits), 32) * 32;
+    const int splits = cdiv(rows_per_group, rps);
+    const long part_elems = static_cast<long>(groups) * H * splits * (D * D + D);
+    float *qkv, *p1, *p2;
+    LB_CUDA(cudaMalloc(&qkv, R * 3 * C * 4));
+    LB_CUDA(cudaMalloc(&p1, part_elems * 4));
+    LB_CUDA(cudaMalloc(&p2, part_elems * 4));
+    selftest_fill_kernel<<<2048, 256>>>(qkv, R * 3 * C, 1u, -1.f, 2.f);
+    LB_CUDA(cudaMemset(p1, 0xFF, part_elems * 4));
+    LB_CUDA(cudaMemset(p2, 0x7F, part_elems * 4));
+    float ms1 = 0, ms2 = 0;
+    for (int v = 0; v < 2; ++v) {
+      for (int it = 0; it < 12; ++it) {
+        if (it == 2) LB_CUDA(cudaEventRecord(e0));
+        if (v == 0)
+          kv_partial_kernel<32><<<dim3(groups, H, splits), 256>>>(qkv, 3 * C, C, 2 * C, 0, rows_per_group, rps, p1);
+        else
+          kv_partial_v2_kernel<32, 8><<<dim3(groups, splits), 256>>>(qkv, 3 * C, C, 0, rows_per_group, rps, p2);
+      }
+      LB_CUDA(cudaEventRecord(e1));
+      LB_CUDA(cudaEventSynchronize(e1));
+      LB_CUDA(cudaEventElapsedTime(v == 0 ? &ms1 : &ms2, e0, e1));
+    }
+    LB_CUDA(cudaGetLastError());
+    unsigned long long nd = 0;
+    LB_TRY(diff(p1, p2, part_elems, &nd));
+    say("kv_partial: v1 %.1f us, v2 %.1f us, differing words %llu of %ld -> %s\n", ms1 * 100.f, ms2 * 100.f, nd,
+        part_elems, nd == 0 ? "IDENTICAL" : "DIFFERENT");
+    failures += nd != 0;
+    cudaFree(qkv); cudaFree(p1); cudaFree(p2);
+  }
+  {  // ---- stem: 16 images 480 x 640
+    const int N = 16, Hh = 480, Ww = 640, CO = 128;
+    const long pix = static_cast<long>(N) * (Hh / 2) * (Ww / 2);
+    float *img, *wt, *sc, *sh;
+    __half *h1, *l1, *h2, *l2;
+    LB_CUDA(cudaMalloc(&img, static_cast<long>(N) * Hh * Ww * 4));
+    LB_CUDA(cudaMalloc(&wt, 49 * CO * 4));
+    LB_CUDA(cudaMalloc(&sc, CO * 4));
+    LB_CUDA(cudaMalloc(&sh, CO * 4));
+    LB_CUDA(cudaMalloc(&h1, pix * CO * 2)); LB_CUDA(cudaMalloc(&l1, pix * CO * 2));
+    LB_CUDA(cudaMalloc(&h2, pix * CO * 2)); LB_CUDA(cudaMalloc(&l2, pix * CO * 2));
+    selftest_fill_kernel<<<2048, 256>>>(img, static_cast<long>(N) * Hh * Ww, 2u, 0.f, 1.f);
+    selftest_fill_kernel<<<32, 256>>>(wt, 49 * CO, 3u, -0.3f, 0.3f);
+    selftest_fill_kernel<<<1, 128>>>(sc, CO, 4u, 0.5f, 1.5f);
+    selftest_fill_kernel<<<1, 128>>>(sh, CO, 5u, -0.2f, 0.2f);
+    LB_CUDA(cudaMemset(h1, 0xFF, pix * CO * 2)); LB_CUDA(cudaMemset(h2, 0x7F, pix * CO * 2));
+    LB_CUDA(cudaMemset(l1, 0xFF, pix * CO * 2)); LB_CUDA(cudaMemset(l2, 0x7F, pix * CO * 2));
+    float ms1 = 0, ms2 = 0;
+    for (int v = 0; v < 2; ++v) {
+      for (int it = 0; it < 7; ++it) {
+        if (it == 2) LB_CUDA(cudaEventRecord(e0));
+        if (v == 0)
+          conv_stem7x7_kernel<128><<<dim3(cdiv(Ww / 2, 128), Hh / 2, N), 128>>>(img, Hh, Ww, wt, sc, sh, h1, l1, CO);
+        else
+          conv_stem7x7_v2_kernel<128><<<dim3(cdiv(Ww / 2, 256), Hh / 2, N), 128>>>(img, Hh, Ww, wt, sc, sh, h2, l2, CO);
+      }
+      LB_CUDA(cudaEventRecord(e1));
+      LB_CUDA(cudaEventSynchronize(e1));
+      LB_CUDA(cudaEventElapsedTime(v == 0 ? &ms1 : &ms2, e0, e1));
+    }
+    LB_CUDA(cudaGetLastError());
+    unsigned long long nd_h = 0, nd_l = 0;
+    LB_TRY(diff(h1, h2, pix * CO / 2, &nd_h));
+    LB_TRY(diff(l1, l2, pix * CO / 2, &nd_l));
+    say("stem7x7: v1 %.1f us, v2 %.1f us, differing words hi %llu lo %llu of %ld -> %s\n", ms1 * 200.f, ms2 * 200.f,
+        nd_h, nd_l, pix * CO / 2, (nd_h | nd_l) == 0 ? "IDENTICAL" : "DIFFERENT");
+    failures += (nd_h | nd_l) != 0;
+    cudaFree(img); cudaFree(wt); cudaFree(sc); cudaFree(sh);
+    cudaFree(h1); cudaFree(l1); cudaFree(h2); cudaFree(l2);
+  }
+  cudaFree(d_ndiff);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return failures ? fail("lb_selftest: %d kernel pair(s) differ", failures) : 0;
 }
 
 int lb_split_planes(const float* x, long rows, int cols, int ld_x, void* hi, void* lo, int ld_pl, int col0,
@@ -708,8 +854,13 @@ int lb_backbone_forward(const LbBackboneWeights* w, const float* images, int N, 
   const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8;
 
   // stem: conv 7x7 s2 + BN + ReLU                                                  [resnet_fpn.py:101]
-  conv_stem7x7_kernel<128><<<dim3(cdiv(W2, 128), H2, N), 128, 0, st>>>(images, H, W, w->stem_wt, w->stem_scale,
-                                                                        w->stem_shift, B.s0.hi, B.s0.lo, B.s0.ld);
+  if (use_v2(1)) {
+    conv_stem7x7_v2_kernel<128><<<dim3(cdiv(W2, 256), H2, N), 128, 0, st>>>(images, H, W, w->stem_wt, w->stem_scale,
+                                                                            w->stem_shift, B.s0.hi, B.s0.lo, B.s0.ld);
+  } else {
+    conv_stem7x7_kernel<128><<<dim3(cdiv(W2, 128), H2, N), 128, 0, st>>>(images, H, W, w->stem_wt, w->stem_scale,
+                                                                          w->stem_shift, B.s0.hi, B.s0.lo, B.s0.ld);
+  }
   LB_LAUNCHED();
   auto conv = [&](const LbConvWeights& cw, const BbBuf& in, int hin, int win, int act, const BbBuf* res,
                   const BbBuf* up, int uph, int upw, const BbBuf* out, float* of32, int f32ld) -> int {

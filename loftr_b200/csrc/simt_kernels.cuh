@@ -181,6 +181,61 @@ __global__ void __launch_bounds__(256) kv_partial_kernel(const float* __restrict
   if ((tid & 7) == 0) out[D * D + d] = ks;
 }
 
+// Second version of the (group, split) partial: one block covers ALL heads of a token range, so every token's
+// K|V segment (2*H*D contiguous floats) is fetched as one coalesced 2 KB read instead of 2*H separate 128-byte
+// pieces; warp = head, lane = v column, 32 accumulators (one per d) per lane.  Same summation order per output
+// element as kv_partial_kernel (sequential over tokens) -> bit-identical partials.
+template <int D, int H>
+__global__ void __launch_bounds__(32 * H) kv_partial_v2_kernel(const float* __restrict__ qkv, int ld, int k_col0,
+                                                               long row_base, int rows_per_group, int rows_per_split,
+                                                               float* __restrict__ part) {
+  static_assert(D == 32 && H == 8, "coarse head layout");
+  constexpr int C = D * H;      // 256
+  constexpr int TOK = 16;
+  __shared__ __align__(16) float sKV[TOK][2 * C];   // K | V of 16 tokens: 32 KB
+  const int g = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
+  const int tid = threadIdx.x, hd = tid >> 5, lane = tid & 31;
+  float acc[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) acc[d] = 0.f;
+  float ks = 0.f;
+  const int s_begin = split * rows_per_split;
+  const int s_end = min(s_begin + rows_per_split, rows_per_group);
+  for (int s0 = s_begin; s0 < s_end; s0 += TOK) {
+#pragma unroll
+    for (int i = 0; i < (TOK * 2 * C / 4) / (32 * H); ++i) {   // 8 float4 per thread
+      const int idx = tid + i * 32 * H;
+      const int tok = idx / (2 * C / 4), c4 = idx % (2 * C / 4);
+      const int srow = s0 + tok;
+      float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (srow < s_end) {
+        const float* rowp = qkv + (row_base + static_cast<long>(g) * rows_per_group + srow) * ld + k_col0;
+        v4 = *reinterpret_cast<const float4*>(rowp + c4 * 4);
+      }
+      *reinterpret_cast<float4*>(&sKV[tok][c4 * 4]) = v4;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int tok = 0; tok < TOK; ++tok) {
+      const float v = sKV[tok][C + hd * D + lane];
+      ks += sKV[tok][hd * D + lane];
+#pragma unroll
+      for (int d4 = 0; d4 < D / 4; ++d4) {
+        const float4 k4 = *reinterpret_cast<const float4*>(&sKV[tok][hd * D + d4 * 4]);
+        acc[4 * d4] = fmaf(k4.x, v, acc[4 * d4]);
+        acc[4 * d4 + 1] = fmaf(k4.y, v, acc[4 * d4 + 1]);
+        acc[4 * d4 + 2] = fmaf(k4.z, v, acc[4 * d4 + 2]);
+        acc[4 * d4 + 3] = fmaf(k4.w, v, acc[4 * d4 + 3]);
+      }
+    }
+    __syncthreads();
+  }
+  float* out = part + ((static_cast<long>(g) * H + hd) * nsplit + split) * (D * D + D);
+#pragma unroll
+  for (int d = 0; d < D; ++d) out[d * D + lane] = acc[d];
+  out[D * D + lane] = ks;
+}
+
 // kv[g,h,:] = sum over splits (fixed order).  Layout of kv: [g][h][D*D + D] (KV then Ksum).
 __global__ void kv_merge_kernel(const float* __restrict__ part, int nsplit, int per, float* __restrict__ kv,
                                 long total) {
@@ -734,6 +789,103 @@ __global__ void fine_match_kernel(const FineMatchParams p) {
     const float half_w = static_cast<float>(p.W / 2);
     p.mkpts1_f[2 * m] = p.mkpts1_c[2 * m] + ex * half_w * sx;
     p.mkpts1_f[2 * m + 1] = p.mkpts1_c[2 * m + 1] + ey * half_w * sy;
+  }
+}
+
+// Second version of the stem: two horizontally adjacent output pixels per thread share every weight fetch
+// (7 x 9 input patch in registers), halving the shared-memory reads per FMA.
+template <int COUT>
+__global__ void __launch_bounds__(128) conv_stem7x7_v2_kernel(const float* __restrict__ img, int H, int W,
+                                                              const float* __restrict__ wt /*[49][COUT]*/,
+                                                              const float* __restrict__ scale,
+                                                              const float* __restrict__ shift,
+                                                              __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                                              int out_ld) {
+  __shared__ __align__(16) float s_w[49 * COUT];
+  __shared__ float s_sc[COUT], s_sh[COUT];
+  for (int i = threadIdx.x; i < 49 * COUT; i += blockDim.x) s_w[i] = wt[i];
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
+    s_sc[i] = scale[i];
+    s_sh[i] = shift[i];
+  }
+  __syncthreads();
+  const int Ho = H / 2, Wo = W / 2;
+  const int n = blockIdx.z;
+  const int oy = blockIdx.y;
+  const int ox = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (ox >= Wo) return;
+  const bool two = ox + 1 < Wo;
+  float in[7][9];
+#pragma unroll
+  for (int ky = 0; ky < 7; ++ky) {
+    const int iy = oy * 2 + ky - 3;
+#pragma unroll
+    for (int kx = 0; kx < 9; ++kx) {
+      const int ix = ox * 2 + kx - 3;
+      in[ky][kx] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? img[(static_cast<long>(n) * H + iy) * W + ix] : 0.f;
+    }
+  }
+  const long pix = (static_cast<long>(n) * Ho + oy) * Wo + ox;
+#pragma unroll 1
+  for (int c0 = 0; c0 < COUT; c0 += 16) {
+    float a0[16], a1[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      a0[j] = 0.f;
+      a1[j] = 0.f;
+    }
+#pragma unroll
+    for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        const float v0 = in[ky][kx], v1 = in[ky][kx + 2];
+        const float4* wp = reinterpret_cast<const float4*>(&s_w[(ky * 7 + kx) * COUT + c0]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 w4 = wp[j];
+          a0[4 * j] = fmaf(v0, w4.x, a0[4 * j]);
+          a0[4 * j + 1] = fmaf(v0, w4.y, a0[4 * j + 1]);
+          a0[4 * j + 2] = fmaf(v0, w4.z, a0[4 * j + 2]);
+          a0[4 * j + 3] = fmaf(v0, w4.w, a0[4 * j + 3]);
+          a1[4 * j] = fmaf(v1, w4.x, a1[4 * j]);
+          a1[4 * j + 1] = fmaf(v1, w4.y, a1[4 * j + 1]);
+          a1[4 * j + 2] = fmaf(v1, w4.z, a1[4 * j + 2]);
+          a1[4 * j + 3] = fmaf(v1, w4.w, a1[4 * j + 3]);
+        }
+      }
+    }
+    // 16 channels = 32 bytes per plane per pixel
+    uint32_t h0[8], l0[8], h1[8], l1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __half ha, la, hb, lb2;
+      float x = fmaxf(fmaf(a0[2 * j], s_sc[c0 + 2 * j], s_sh[c0 + 2 * j]), 0.f);
+      float y = fmaxf(fmaf(a0[2 * j + 1], s_sc[c0 + 2 * j + 1], s_sh[c0 + 2 * j + 1]), 0.f);
+      split_f16(x, ha, la);
+      split_f16(y, hb, lb2);
+      h0[j] = static_cast<uint32_t>(__half_as_ushort(ha)) | (static_cast<uint32_t>(__half_as_ushort(hb)) << 16);
+      l0[j] = static_cast<uint32_t>(__half_as_ushort(la)) | (static_cast<uint32_t>(__half_as_ushort(lb2)) << 16);
+      x = fmaxf(fmaf(a1[2 * j], s_sc[c0 + 2 * j], s_sh[c0 + 2 * j]), 0.f);
+      y = fmaxf(fmaf(a1[2 * j + 1], s_sc[c0 + 2 * j + 1], s_sh[c0 + 2 * j + 1]), 0.f);
+      split_f16(x, ha, la);
+      split_f16(y, hb, lb2);
+      h1[j] = static_cast<uint32_t>(__half_as_ushort(ha)) | (static_cast<uint32_t>(__half_as_ushort(hb)) << 16);
+      l1[j] = static_cast<uint32_t>(__half_as_ushort(la)) | (static_cast<uint32_t>(__half_as_ushort(lb2)) << 16);
+    }
+    uint4* ph = reinterpret_cast<uint4*>(out_hi + pix * out_ld + c0);
+    uint4* pl = reinterpret_cast<uint4*>(out_lo + pix * out_ld + c0);
+    ph[0] = make_uint4(h0[0], h0[1], h0[2], h0[3]);
+    ph[1] = make_uint4(h0[4], h0[5], h0[6], h0[7]);
+    pl[0] = make_uint4(l0[0], l0[1], l0[2], l0[3]);
+    pl[1] = make_uint4(l0[4], l0[5], l0[6], l0[7]);
+    if (two) {
+      uint4* qh = reinterpret_cast<uint4*>(out_hi + (pix + 1) * out_ld + c0);
+      uint4* ql = reinterpret_cast<uint4*>(out_lo + (pix + 1) * out_ld + c0);
+      qh[0] = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+      qh[1] = make_uint4(h1[4], h1[5], h1[6], h1[7]);
+      ql[0] = make_uint4(l1[0], l1[1], l1[2], l1[3]);
+      ql[1] = make_uint4(l1[4], l1[5], l1[6], l1[7]);
+    }
   }
 }
 
