@@ -189,11 +189,13 @@ static int kernel_mode(int tag) {
 
 // Second-generation CUDA-core kernels (kv_partial_v2, conv_stem7x7_v2).  They produce bit-identical results to the
 // first versions (checked on the device by lb_selftest, which also times both); LOFTR_B200_V2=0|1 overrides.
+// Measured (profiles/r1_selftest_v2_kernels.log): the stem v2 is 29 % faster (582 vs 816 us at batch 8) -> default;
+// kv_partial v2 is slower (129 vs 110 us: its 32-accumulator inner loop is shared-memory-read bound) -> v1 stays.
 #ifndef LB_KV_V2_DEFAULT
 #define LB_KV_V2_DEFAULT 0
 #endif
 #ifndef LB_STEM_V2_DEFAULT
-#define LB_STEM_V2_DEFAULT 0
+#define LB_STEM_V2_DEFAULT 1
 #endif
 static bool use_v2(int which /*0 = kv_partial, 1 = stem*/) {
   static int forced = -2;
