@@ -42,6 +42,10 @@ extern "C" {
 int lb_version(void);
 /* k-block (in elements) the library was built with: convolution weight planes pad Cin per tap to a multiple of it */
 int lb_block_k(void);
+/* K layout of a convolution with `cin` input channels: `cin_blocks` 64-channel blocks per tap in the main weight
+ * planes, plus `rem_channels` (0, or 1..16 when cin = 64*cin_blocks + rem, e.g. 196 = 3*64 + 4) channels per tap that
+ * go into the remainder planes of LbConvWeights. */
+int lb_conv_layout(int cin, int* cin_blocks /*host*/, int* rem_channels /*host*/);
 const char* lb_last_error(void);
 /* number of kernels this library has launched in this process (for bench.py's gpu_launches) */
 long long lb_launch_count(void);
@@ -77,11 +81,15 @@ int lb_coarse_prep(const float* feat, int nhwc, const float* pe, int n_img, int 
 
 /* ResNetFPN_8_2 local-feature CNN on tensor cores (reference src/loftr/backbone/resnet_fpn.py:43-118; SURVEY.md
  * §8(f) rank 1).  One LbConvWeights per Conv2d(+BatchNorm2d in eval mode, folded to scale/shift; scale = 1,
- * shift = 0 for a bare convolution).  Weight planes: [cout, k*k * ceil(cin/64)*64] = for every tap the cin
- * channels zero-padded to a multiple of 64 (tap-major), fp16 hi/lo. */
+ * shift = 0 for a bare convolution).  Weight planes (fp16 hi/lo, tap-major), with (cin_blocks, rem) =
+ * lb_conv_layout(cin): main [cout, k*k * cin_blocks*64] = for every tap the first cin_blocks*64 channels (zero padded
+ * when rem == 0 and cin is not a multiple of 64); remainder [cout, k*k * 16] = for every tap channels
+ * cin_blocks*64 .. cin-1 zero-padded to 16 (NULL when rem == 0). */
 typedef struct LbConvWeights {
   const void* w_hi;
   const void* w_lo;
+  const void* wr_hi;   /* remainder planes or NULL */
+  const void* wr_lo;
   const float* scale;  /* [cout] */
   const float* shift;  /* [cout] */
   int cin, cout, ksize, stride;
@@ -115,6 +123,8 @@ int lb_backbone_forward(const LbBackboneWeights* w /*host*/, const float* images
 typedef struct LbEncoderLayerWeights {
   const void* wqkv_hi; /* [3C, C]: rows = q_proj.weight, k_proj.weight, v_proj.weight */
   const void* wqkv_lo;
+  const void* wkv_hi;  /* optional (coarse, D = 32) [2C, C]: the k and v rows of wqkv regrouped in blocks of 4 heads, */
+  const void* wkv_lo;  /* [k heads 0-3; v heads 0-3; k heads 4-7; v heads 4-7]: B operand of the fused k|v projection */
   const void* wm_hi;   /* [C, C]   merge.weight */
   const void* wm_lo;
   const void* w1_hi;   /* [2C, 2C] mlp.0.weight */

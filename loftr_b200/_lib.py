@@ -29,12 +29,13 @@ c_size_t = C.c_size_t
 
 class LbEncoderLayerWeights(C.Structure):
     _fields_ = [(n, c_void_p) for n in (
-        "wqkv_hi", "wqkv_lo", "wm_hi", "wm_lo", "w1_hi", "w1_lo", "w2_hi", "w2_lo",
+        "wqkv_hi", "wqkv_lo", "wkv_hi", "wkv_lo", "wm_hi", "wm_lo", "w1_hi", "w1_lo", "w2_hi", "w2_lo",
         "ln1_g", "ln1_b", "ln2_g", "ln2_b")] + [(n, c_float) for n in ("s_qkv", "s_m", "s_1", "s_2")]
 
 
 class LbConvWeights(C.Structure):
-    _fields_ = [("w_hi", c_void_p), ("w_lo", c_void_p), ("scale", c_void_p), ("shift", c_void_p),
+    _fields_ = [("w_hi", c_void_p), ("w_lo", c_void_p), ("wr_hi", c_void_p), ("wr_lo", c_void_p),
+                ("scale", c_void_p), ("shift", c_void_p),
                 ("cin", c_int), ("cout", c_int), ("ksize", c_int), ("stride", c_int)]
 
 
@@ -90,10 +91,11 @@ class LbFineMatchArgs(C.Structure):
     ]
 
 
-# name -> (restype, argtypes); the same list is what tests/test_abi.py checks against the header.
+# name -> (restype, argtypes); the same list is what tests/test_host.py checks against the header.
 SIGNATURES = {
     "lb_version": (c_int, []),
     "lb_block_k": (c_int, []),
+    "lb_conv_layout": (c_int, [c_int, C.POINTER(c_int), C.POINTER(c_int)]),
     "lb_last_error": (C.c_char_p, []),
     "lb_launch_count": (C.c_longlong, []),
     "lb_selftest": (c_int, [C.c_char_p, c_int]),

@@ -53,9 +53,10 @@ static int fail(const char* fmt, ...) {
 // Optional per-launch CUDA-event timing of the tensor-core kernels (bench.py's roofline leg): events are
 // recorded on the launching stream right around the kernel, and only while timing is enabled.
 enum Tag { TAG_GEMM_TEST = 0, TAG_PROJ, TAG_MERGE_LN, TAG_MLP1, TAG_MLP2_LN, TAG_SCORE_LSE, TAG_SCORE_ARGMAX,
-           TAG_FINE_MERGE, TAG_CONV, TAG_COUNT };
+           TAG_FINE_MERGE, TAG_CONV, TAG_KV, TAG_QATTN, TAG_COUNT };
 static const char* kTagNames[TAG_COUNT] = {"gemm_test", "proj_act", "merge_ln", "mlp1_relu", "mlp2_ln_res",
-                                           "score_lse", "score_argmax", "fine_merge", "backbone_conv"};
+                                           "score_lse", "score_argmax", "fine_merge", "backbone_conv",
+                                           "tf_kv_proj_fused", "tf_q_attn_fused"};
 struct TimingRec {
   cudaEvent_t e0, e1;
   int tag;
@@ -68,22 +69,33 @@ static std::mutex g_timing_mu;
 // caller's (e.g. torch's).  Every entry point therefore binds the calling thread to the device that owns the
 // buffers it was given -- otherwise a process working on cuda:1 would launch on device 0 through the legacy
 // default stream.
+// The previous device of the calling thread is restored when the entry point returns (RAII), so a caller whose
+// current device differs from the buffers' device is left undisturbed.
 constexpr int kMaxDevices = 64;
-static int bind_device_of(const void* dev_ptr) {
-  if (!dev_ptr) return fail("null device pointer");
-  cudaPointerAttributes attr;
-  cudaError_t e = cudaPointerGetAttributes(&attr, dev_ptr);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    return fail("no usable CUDA device for this buffer (%s); loftr_b200 has no CPU fallback", cudaGetErrorString(e));
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  int bind(const void* dev_ptr) {
+    if (!dev_ptr) return fail("null device pointer");
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, dev_ptr);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail("no usable CUDA device for this buffer (%s); loftr_b200 has no CPU fallback", cudaGetErrorString(e));
+    }
+    if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)
+      return fail("expected a CUDA device pointer; loftr_b200 has no CPU fallback");
+    LB_CUDA(cudaGetDevice(&prev));
+    if (prev != attr.device) {
+      LB_CUDA(cudaSetDevice(attr.device));
+      switched = true;
+    }
+    return 0;
   }
-  if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)
-    return fail("expected a CUDA device pointer; loftr_b200 has no CPU fallback");
-  int cur = -1;
-  LB_CUDA(cudaGetDevice(&cur));
-  if (cur != attr.device) LB_CUDA(cudaSetDevice(attr.device));
-  return 0;
-}
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
 
 static int device_check(int* sm_count) {
   static std::mutex mu;
@@ -123,18 +135,21 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 // fp16 plane viewed as [batches][rows][K] with row stride ld and batch stride bs (elements);
 // box = 64 (K) x box_rows x 1, 128-byte swizzle, out-of-range elements read as zero.
+static CUtensorMapSwizzle swizzle_for(int box_k) {
+  return box_k * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : box_k * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
 static int make_map(CUtensorMap* m, const void* base, long K, long rows, long batches, long ld, long bs,
-                    int box_rows) {
+                    int box_rows, int box_k = kBlockK) {
   auto enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail("plane pointer not 16-byte aligned");
   if ((ld * 2) % 16 != 0 || (bs * 2) % 16 != 0) return fail("plane strides must be multiples of 8 elements");
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batches)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld * 2), static_cast<cuuint64_t>((bs > 0 ? bs : rows * ld) * 2)};
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_k), static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, kBlockK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(box_k),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
@@ -143,7 +158,8 @@ static int make_map(CUtensorMap* m, const void* base, long K, long rows, long ba
 
 // NHWC fp16 plane viewed as [N][H][W][C] (row stride ld elements); box = 64 channels x (16*stride) x (8*stride)
 // x 1 with element strides (1, stride, stride, 1): an 8 x 16 patch of (strided) pixels per load.
-static int make_map_nhwc(CUtensorMap* m, const void* base, int C, int W, int H, int N, long ld, int stride) {
+static int make_map_nhwc(CUtensorMap* m, const void* base, int C, int W, int H, int N, long ld, int stride,
+                         int box_c = kBlockK) {
   auto enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail("plane pointer not 16-byte aligned");
@@ -152,11 +168,11 @@ static int make_map_nhwc(CUtensorMap* m, const void* base, int C, int W, int H, 
                         static_cast<cuuint64_t>(N)};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(ld * 2), static_cast<cuuint64_t>(ld * 2 * W),
                            static_cast<cuuint64_t>(ld * 2 * W) * H};
-  cuuint32_t box[4] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(kConvTileW * stride),
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(kConvTileW * stride),
                        static_cast<cuuint32_t>(kConvTileH * stride), 1};
   cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, kBlockK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(box_c),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (NHWC) failed with CUresult %d", static_cast<int>(r));
@@ -197,6 +213,16 @@ static int kernel_mode(int tag) {
 #ifndef LB_STEM_V2_DEFAULT
 #define LB_STEM_V2_DEFAULT 1
 #endif
+// Fused linear attention (EpiKv / EpiAttn epilogues, coarse transformer): LOFTR_B200_FUSED_ATTN=0 restores the
+// first-generation path (fp32 q/k/v in HBM + kv_partial / attn_apply kernels) for A/B measurements.
+static bool use_fused_attn() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LOFTR_B200_FUSED_ATTN");
+    v = e ? (atoi(e) != 0 ? 1 : 0) : 1;
+  }
+  return v == 1;
+}
 static bool use_v2(int which /*0 = kv_partial, 1 = stem*/) {
   static int forced = -2;
   if (forced == -2) {
@@ -207,9 +233,13 @@ static bool use_v2(int which /*0 = kv_partial, 1 = stem*/) {
   return which == 0 ? (LB_KV_V2_DEFAULT != 0) : (LB_STEM_V2_DEFAULT != 0);
 }
 
+struct GemmMaps {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;      // 64-element k-blocks
+  CUtensorMap ar_hi, ar_lo, br_hi, br_lo;  // convolution channel remainder (16-element boxes); copies of the above if unused
+};
+
 template <int BN, class Epi, bool kDual, int kMode>
-static int launch_raw(int tag, const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
-                      const CUtensorMap& mb_lo, const GemmShape& s, const typename Epi::Params& ep, int sms,
+static int launch_raw(int tag, const GemmMaps& maps, const GemmShape& s, const typename Epi::Params& ep, int sms,
                       cudaStream_t st) {
   constexpr int kCluster = kMode == 0 ? 1 : 2;
   using S = GemmSmem<BN, kMode == 2>;
@@ -246,7 +276,8 @@ static int launch_raw(int tag, const CUtensorMap& ma_hi, const CUtensorMap& ma_l
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  LB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, s, ep));
+  LB_CUDA(cudaLaunchKernelEx(&cfg, kern, maps.a_hi, maps.a_lo, maps.b_hi, maps.b_lo, maps.ar_hi, maps.ar_lo, maps.br_hi,
+                             maps.br_lo, s, ep));
   LB_LAUNCHED();
   if (g_timing) {
     LB_CUDA(cudaEventRecord(rec.e1, st));
@@ -274,61 +305,92 @@ static int launch_gemm(int tag, const Planes& A, const Planes& B, int batches, i
   if (n_chunks <= 0 || n_chunks > s.n_tiles) n_chunks = s.n_tiles;
   s.tiles_per_chunk = (s.n_tiles + n_chunks - 1) / n_chunks;
   s.n_chunks = (s.n_tiles + s.tiles_per_chunk - 1) / s.tiles_per_chunk;
-  s.conv = ConvGeom{0, 0, 0, 0, 0, 0};
+  s.conv = ConvGeom{0, 0, 0, 0, 0, 0, 0, 0, 0};
 
   const int mode = s.m_tiles >= 2 ? kernel_mode(tag) : 0;
   const int cl = mode == 0 ? 1 : 2;
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  LB_TRY(make_map(&ma_hi, A.hi, K, M, batches, A.ld, A.batch_stride, kBlockM));
-  LB_TRY(make_map(&ma_lo, A.lo, K, M, batches, A.ld, A.batch_stride, kBlockM));
+  GemmMaps mp;
+  LB_TRY(make_map(&mp.a_hi, A.hi, K, M, batches, A.ld, A.batch_stride, kBlockM));
+  LB_TRY(make_map(&mp.a_lo, A.lo, K, M, batches, A.ld, A.batch_stride, kBlockM));
   const int bb = s.b_batched ? batches : 1;
-  LB_TRY(make_map(&mb_hi, B.hi, K, N, bb, B.ld, B.batch_stride, BN / cl));
-  LB_TRY(make_map(&mb_lo, B.lo, K, N, bb, B.ld, B.batch_stride, BN / cl));
-  if (mode == 2) return launch_raw<BN, Epi, false, 2>(tag, ma_hi, ma_lo, mb_hi, mb_lo, s, ep, sms, st);
-  if (mode == 1) return launch_raw<BN, Epi, false, 1>(tag, ma_hi, ma_lo, mb_hi, mb_lo, s, ep, sms, st);
-  return launch_raw<BN, Epi, false, 0>(tag, ma_hi, ma_lo, mb_hi, mb_lo, s, ep, sms, st);
+  LB_TRY(make_map(&mp.b_hi, B.hi, K, N, bb, B.ld, B.batch_stride, BN / cl));
+  LB_TRY(make_map(&mp.b_lo, B.lo, K, N, bb, B.ld, B.batch_stride, BN / cl));
+  mp.ar_hi = mp.a_hi; mp.ar_lo = mp.a_lo; mp.br_hi = mp.b_hi; mp.br_lo = mp.b_lo;
+  if (mode == 2) return launch_raw<BN, Epi, false, 2>(tag, mp, s, ep, sms, st);
+  if (mode == 1) return launch_raw<BN, Epi, false, 1>(tag, mp, s, ep, sms, st);
+  return launch_raw<BN, Epi, false, 0>(tag, mp, s, ep, sms, st);
 }
 
 // Implicit-GEMM convolution launch: in = NHWC planes [N, H_in, W_in, ld_in] with Cin valid channels; weights =
-// planes [Cout, taps * cin_blocks * 64] (zero padded per tap); out pixel grid H_out x W_out.
+// main planes [Cout, taps * cin_blocks * 64] (+ remainder planes [Cout, taps * 16], see lb_conv_layout); out pixel
+// grid H_out x W_out.
 struct ConvDesc {
   int N, H_in, W_in, Cin, H_out, W_out, Cout, ksize, stride, pad;
 };
+// K layout of a convolution's implicit GEMM: `cin_blocks` 64-channel blocks per tap, plus `rem` (<= 16) remainder
+// channels per tap that travel as 16-channel boxes (gemm_split.cuh ConvGeom).
+static void conv_layout(int cin, int* cin_blocks, int* rem) {
+  static int enabled = -1;   // LOFTR_B200_CONV_REM=0: pad every tap to whole 64-channel blocks (first-generation layout)
+  if (enabled < 0) {
+    const char* e = getenv("LOFTR_B200_CONV_REM");
+    enabled = e ? (atoi(e) != 0 ? 1 : 0) : 1;
+  }
+  const int r = cin % kBlockK;
+  if (enabled && kBlockK == 64 && cin > kBlockK && r > 0 && r <= kRemChannels) {
+    *cin_blocks = cin / kBlockK;
+    *rem = r;
+  } else {
+    *cin_blocks = (cin + kBlockK - 1) / kBlockK;
+    *rem = 0;
+  }
+}
 template <int BN>
-static int launch_conv(const Planes& in, const Planes& wgt, const ConvDesc& d, const typename EpiConv<BN>::Params& ep_in,
-                       cudaStream_t st) {
+static int launch_conv(const Planes& in, const Planes& wgt, const Planes& wgt_rem, const ConvDesc& d,
+                       const typename EpiConv<BN>::Params& ep_in, cudaStream_t st) {
   using Epi = EpiConv<BN>;
   int sms = 0;
   LB_TRY(device_check(&sms));
   GemmShape s;
-  const int cin_blocks = (d.Cin + kBlockK - 1) / kBlockK;
+  int cin_blocks = 0, rem = 0;
+  conv_layout(d.Cin, &cin_blocks, &rem);
+  const int taps = d.ksize * d.ksize;
   const int tiles_h = (d.H_out + kConvTileH - 1) / kConvTileH;
   const int tiles_w = (d.W_out + kConvTileW - 1) / kConvTileW;
   s.batches = d.N;
   s.M = tiles_h * tiles_w * kBlockM;
   s.N = d.Cout;
-  s.K = d.ksize * d.ksize * cin_blocks * kBlockK;
+  s.K = taps * cin_blocks * kBlockK;
   s.b_batched = 0;
   s.m_tiles = tiles_h * tiles_w;
   s.n_tiles = (d.Cout + BN - 1) / BN;
   s.n_chunks = s.n_tiles;
   s.tiles_per_chunk = 1;
-  s.conv = ConvGeom{1, tiles_w, d.stride, d.pad, d.ksize, cin_blocks};
+  const int rem_groups = rem ? (taps + kRemTapsPerStage - 1) / kRemTapsPerStage : 0;
+  s.conv = ConvGeom{1, tiles_w, d.stride, d.pad, d.ksize, cin_blocks, taps, taps * cin_blocks, rem_groups};
+  if (rem && (!wgt_rem.hi || !wgt_rem.lo)) return fail("convolution with Cin=%d needs remainder weight planes", d.Cin);
   const int mode = s.m_tiles >= 2 ? kernel_mode(TAG_CONV) : 0;
   const int cl = mode == 0 ? 1 : 2;
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  LB_TRY(make_map_nhwc(&ma_hi, in.hi, d.Cin, d.W_in, d.H_in, d.N, in.ld, d.stride));
-  LB_TRY(make_map_nhwc(&ma_lo, in.lo, d.Cin, d.W_in, d.H_in, d.N, in.ld, d.stride));
-  LB_TRY(make_map(&mb_hi, wgt.hi, s.K, d.Cout, 1, wgt.ld, 0, BN / cl));
-  LB_TRY(make_map(&mb_lo, wgt.lo, s.K, d.Cout, 1, wgt.ld, 0, BN / cl));
+  GemmMaps mp;
+  LB_TRY(make_map_nhwc(&mp.a_hi, in.hi, d.Cin, d.W_in, d.H_in, d.N, in.ld, d.stride));
+  LB_TRY(make_map_nhwc(&mp.a_lo, in.lo, d.Cin, d.W_in, d.H_in, d.N, in.ld, d.stride));
+  LB_TRY(make_map(&mp.b_hi, wgt.hi, s.K, d.Cout, 1, wgt.ld, 0, BN / cl));
+  LB_TRY(make_map(&mp.b_lo, wgt.lo, s.K, d.Cout, 1, wgt.ld, 0, BN / cl));
+  if (rem) {
+    LB_TRY(make_map_nhwc(&mp.ar_hi, in.hi, d.Cin, d.W_in, d.H_in, d.N, in.ld, d.stride, kRemChannels));
+    LB_TRY(make_map_nhwc(&mp.ar_lo, in.lo, d.Cin, d.W_in, d.H_in, d.N, in.ld, d.stride, kRemChannels));
+    LB_TRY(make_map(&mp.br_hi, wgt_rem.hi, taps * kRemChannels, d.Cout, 1, wgt_rem.ld, 0, BN / cl, kRemChannels));
+    LB_TRY(make_map(&mp.br_lo, wgt_rem.lo, taps * kRemChannels, d.Cout, 1, wgt_rem.ld, 0, BN / cl, kRemChannels));
+  } else {
+    mp.ar_hi = mp.a_hi; mp.ar_lo = mp.a_lo; mp.br_hi = mp.b_hi; mp.br_lo = mp.b_lo;
+  }
   typename Epi::Params ep = ep_in;
   ep.H_out = d.H_out;
   ep.W_out = d.W_out;
   ep.tiles_w = tiles_w;
   // dual accumulator: EpiConv adds the correction accumulator
-  if (mode == 2) return launch_raw<BN, Epi, true, 2>(TAG_CONV, ma_hi, ma_lo, mb_hi, mb_lo, s, ep, sms, st);
-  if (mode == 1) return launch_raw<BN, Epi, true, 1>(TAG_CONV, ma_hi, ma_lo, mb_hi, mb_lo, s, ep, sms, st);
-  return launch_raw<BN, Epi, true, 0>(TAG_CONV, ma_hi, ma_lo, mb_hi, mb_lo, s, ep, sms, st);
+  if (mode == 2) return launch_raw<BN, Epi, true, 2>(TAG_CONV, mp, s, ep, sms, st);
+  if (mode == 1) return launch_raw<BN, Epi, true, 1>(TAG_CONV, mp, s, ep, sms, st);
+  return launch_raw<BN, Epi, true, 0>(TAG_CONV, mp, s, ep, sms, st);
 }
 
 // number of n-chunks that gives every SM a few work items when a CTA must sweep many n tiles
@@ -371,25 +433,28 @@ struct TfWs {
   __half* h_hi;     // [R, 2C]
   __half* h_lo;
   float* kv;        // [2*n_groups, H, D*D + D]
-  float* kv_part;   // coarse only: [2*n_groups, H, splits, D*D + D]
+  float* kv_part;   // coarse only: max([2*n_groups, H, splits, per], [2*n_groups, m_tiles, H, per]) (split / tile partials)
 };
 constexpr int kKvSplits = 8;
 
-static void carve_tf(Bump& b, TfWs& w, int C, int H, long R, int n_groups, bool coarse) {
+static void carve_tf(Bump& b, TfWs& w, int C, int H, long R, int n_groups, bool coarse, int max_group_rows) {
   const int D = C / H;
-  w.qkv = b.take<float>(static_cast<size_t>(R) * 3 * C);
+  // fp32 q|k|v: the fine (window) transformer and the first-generation coarse path
+  w.qkv = (coarse && use_fused_attn()) ? nullptr : b.take<float>(static_cast<size_t>(R) * 3 * C);
   w.att_hi = b.take<__half>(static_cast<size_t>(R) * C);
   w.att_lo = b.take<__half>(static_cast<size_t>(R) * C);
   w.h_hi = b.take<__half>(static_cast<size_t>(R) * 2 * C);
   w.h_lo = b.take<__half>(static_cast<size_t>(R) * 2 * C);
   w.kv = b.take<float>(static_cast<size_t>(2) * n_groups * H * (D * D + D));
-  w.kv_part = coarse ? b.take<float>(static_cast<size_t>(2) * n_groups * H * kKvSplits * (D * D + D)) : nullptr;
+  const size_t tiles = static_cast<size_t>((max_group_rows + kBlockM - 1) / kBlockM);
+  const size_t parts = tiles > static_cast<size_t>(kKvSplits) ? tiles : static_cast<size_t>(kKvSplits);
+  w.kv_part = coarse ? b.take<float>(static_cast<size_t>(2) * n_groups * H * parts * (D * D + D)) : nullptr;
 }
 
 template <int BN>
 static int tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, const LbTransformerState& st, const TfWs& w,
                          long x_base, long x_rows, int x_group_rows, long s_base, long s_rows, int s_group_rows,
-                         int n_groups_x, bool self_pass, cudaStream_t stream);
+                         int n_groups_x, bool self_pass, bool write_f32, cudaStream_t stream);
 
 
 // ------------------------------------------------------------------------------------------------ backbone
@@ -447,22 +512,31 @@ static int run_conv(const ConvRun& r, int N, cudaStream_t st) {
   d.H_out = (r.H_in + 2 * d.pad - w.ksize) / w.stride + 1;
   d.W_out = (r.W_in + 2 * d.pad - w.ksize) / w.stride + 1;
   d.Cout = w.cout;
-  const int cin_blocks = (w.cin + kBlockK - 1) / kBlockK;
+  int cin_blocks = 0, rem = 0;
+  conv_layout(w.cin, &cin_blocks, &rem);
+  const int taps = w.ksize * w.ksize;
   Planes in{r.in.hi, r.in.lo, r.in.ld, 0};
-  Planes wg{w.w_hi, w.w_lo, static_cast<long>(w.ksize) * w.ksize * cin_blocks * kBlockK, 0};
-  if (w.cout <= 128) {
-    EpiConv<128>::Params ep{w.scale, w.shift, r.act, r.res ? r.res->hi : nullptr, r.res ? r.res->lo : nullptr,
-                            r.res ? r.res->ld : 0, r.up ? r.up->hi : nullptr, r.up ? r.up->lo : nullptr,
-                            r.up ? r.up->ld : 0, r.up_h, r.up_w, r.out ? r.out->hi : nullptr,
-                            r.out ? r.out->lo : nullptr, r.out ? r.out->ld : 0, r.out_f32, r.f32_ld, 0, 0, 0};
-    return launch_conv<128>(in, wg, d, ep, st);
+  Planes wg{w.w_hi, w.w_lo, static_cast<long>(taps) * cin_blocks * kBlockK, 0};
+  Planes wr{w.wr_hi, w.wr_lo, static_cast<long>(taps) * kRemChannels, 0};
+#define LB_CONV_CASE(BN)                                                                                              \
+  {                                                                                                                   \
+    EpiConv<BN>::Params ep{w.scale, w.shift, r.act, r.res ? r.res->hi : nullptr, r.res ? r.res->lo : nullptr,       \
+                           r.res ? r.res->ld : 0, r.up ? r.up->hi : nullptr, r.up ? r.up->lo : nullptr,              \
+                           r.up ? r.up->ld : 0, r.up_h, r.up_w, r.out ? r.out->hi : nullptr,                          \
+                           r.out ? r.out->lo : nullptr, r.out ? r.out->ld : 0, r.out_f32, r.f32_ld, 0, 0, 0};         \
+    return launch_conv<BN>(in, wg, wr, d, ep, st);                                                                    \
   }
-  if (w.cout > 256) return fail("convolutions with more than 256 output channels are not built");
-  EpiConv<256>::Params ep{w.scale, w.shift, r.act, r.res ? r.res->hi : nullptr, r.res ? r.res->lo : nullptr,
-                          r.res ? r.res->ld : 0, r.up ? r.up->hi : nullptr, r.up ? r.up->lo : nullptr,
-                          r.up ? r.up->ld : 0, r.up_h, r.up_w, r.out ? r.out->hi : nullptr,
-                          r.out ? r.out->lo : nullptr, r.out ? r.out->ld : 0, r.out_f32, r.f32_ld, 0, 0, 0};
-  return launch_conv<256>(in, wg, d, ep, st);
+  // output-channel tile: the smallest built N that covers Cout (196 -> 208: 13 x 16, no MMAs on 60 padding columns)
+  static int n208 = -1;   // LOFTR_B200_CONV_N208=0: 256-column tiles for Cout = 196 (first-generation tiling)
+  if (n208 < 0) {
+    const char* e = getenv("LOFTR_B200_CONV_N208");
+    n208 = e ? (atoi(e) != 0 ? 1 : 0) : 1;
+  }
+  if (w.cout <= 128) LB_CONV_CASE(128)
+  if (w.cout <= 208 && n208) LB_CONV_CASE(208)
+  if (w.cout <= 256) LB_CONV_CASE(256)
+#undef LB_CONV_CASE
+  return fail("convolutions with more than 256 output channels are not built");
 }
 
 }  // namespace lb
@@ -474,13 +548,44 @@ using namespace lb;
 template <int BN>
 static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, const LbTransformerState& st,
                              const TfWs& w, long x_base, long x_rows, int x_group_rows, long s_base, long s_rows,
-                             int s_group_rows, int n_groups_x, bool self_pass, cudaStream_t stream) {
+                             int s_group_rows, int n_groups_x, bool self_pass, bool write_f32, cudaStream_t stream) {
   const int D = C / H;
   const long ldc = 2L * C;
   const __half* cat_hi = static_cast<const __half*>(st.cat_hi);
   const __half* cat_lo = static_cast<const __half*>(st.cat_lo);
   const uint8_t* mask = st.mask;
+  const int n_groups_s = static_cast<int>(s_rows / s_group_rows);
+  const int per = D * D + D;
+  if (n_groups_x != n_groups_s && !self_pass) return fail("query / source group counts differ");
+  const bool fused = (D == 32) && use_fused_attn() && lw.wkv_hi != nullptr;
 
+  if constexpr (BN == 256) {
+    if (fused) {
+      // 1-3 fused: k|v projection with the K^T V reduction in its epilogue, then the q projection
+      // with the attention product in its epilogue; q, k, v never reach HBM.   [transformer.py:47-50, linear_attention.py:31-46]
+      const int m_tiles_s = cdiv(s_group_rows, kBlockM);
+      {
+        using Epi = EpiKv<256, 32>;
+        Planes A{cat_hi + s_base * ldc, cat_lo + s_base * ldc, ldc, static_cast<long>(s_group_rows) * ldc};
+        Planes B{lw.wkv_hi, lw.wkv_lo, C, 0};
+        typename Epi::Params ep{mask ? mask + s_base : nullptr, lw.s_qkv, w.kv_part, H};
+        LB_TRY((launch_gemm<256, Epi>(TAG_KV, A, B, n_groups_s, s_group_rows, 2 * C, C, 0, ep, stream)));
+        const long total = static_cast<long>(n_groups_s) * H * per;
+        kv_tile_merge_kernel<<<cdiv(total, 256), 256, 0, stream>>>(w.kv_part, m_tiles_s, H * per, w.kv, total);
+        LB_LAUNCHED();
+      }
+      {
+        using Epi = EpiAttn<256, 32>;
+        Planes A{cat_hi + x_base * ldc, cat_lo + x_base * ldc, ldc, static_cast<long>(x_group_rows) * ldc};
+        Planes B{lw.wqkv_hi, lw.wqkv_lo, C, 0};
+        typename Epi::Params ep{mask ? mask + x_base : nullptr, lw.s_qkv, w.kv, 1e-6f, w.att_hi + x_base * C,
+                                w.att_lo + x_base * C, C};
+        LB_TRY((launch_gemm<256, Epi>(TAG_QATTN, A, B, n_groups_x, x_group_rows, C, C, 0, ep, stream)));
+      }
+    }
+  }
+  if (!fused) {
+  if (!w.qkv) return fail("first-generation attention path needs LOFTR_B200_FUSED_ATTN=0 (no q/k/v workspace was carved)");
   // 1. projections (+ elu+1 feature map + padding mask)      [transformer.py:47-49, linear_attention.py:31-39]
   {
     using Epi = EpiActStore<BN>;
@@ -502,8 +607,6 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
     }
   }
   // 2. KV = K^T V and Ksum per (source group, head)            [linear_attention.py:43-44]
-  const int n_groups_s = static_cast<int>(s_rows / s_group_rows);
-  const int per = D * D + D;
   if (D == 32) {
     const int rps = cdiv(cdiv(s_group_rows, kKvSplits), 32) * 32;
     const int splits = cdiv(s_group_rows, rps);
@@ -524,7 +627,6 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
     LB_LAUNCHED();
   }
   // 3. message = (Q KV) / (Q Ksum + eps) -> planes             [linear_attention.py:45-46]
-  if (n_groups_x != n_groups_s && !self_pass) return fail("query / source group counts differ");
   if (D == 32) {
     const int rpb = 128;
     attn_apply_kernel<32, 8><<<dim3(n_groups_x, cdiv(x_group_rows, rpb)), 256, 0, stream>>>(
@@ -534,12 +636,13 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
                                                                       w.kv, 1e-6f, w.att_hi, w.att_lo, C);
   }
   LB_LAUNCHED();
+  }  // !fused
   // 4. merge + norm1 -> cat[:, C:2C]                            [transformer.py:51-52]
   {
     using Epi = EpiLayerNorm<BN>;
     Planes A{w.att_hi + x_base * C, w.att_lo + x_base * C, C, 0};
     Planes B{lw.wm_hi, lw.wm_lo, C, 0};
-    typename Epi::Params ep{lw.ln1_g, lw.ln1_b, 1e-5f, nullptr, 0, nullptr, 0,
+    typename Epi::Params ep{lw.ln1_g, lw.ln1_b, 1e-5f, nullptr, 0, nullptr, nullptr, 0, nullptr, 0,
                             static_cast<__half*>(st.cat_hi) + x_base * ldc,
                             static_cast<__half*>(st.cat_lo) + x_base * ldc, static_cast<int>(ldc), C, lw.s_m};
     LB_TRY((launch_gemm<BN, Epi>(TAG_MERGE_LN, A, B, 1, static_cast<int>(x_rows), C, C, 0, ep, stream)));
@@ -553,13 +656,16 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
                             static_cast<int>(ldc), 0, lw.s_1};
     LB_TRY((launch_gemm<BN, Epi>(TAG_MLP1, A, B, 1, static_cast<int>(x_rows), 2 * C, 2 * C, 0, ep, stream)));
   }
-  // 6. mlp[2] + norm2 + residual -> x_f32 and cat[:, 0:C]        [transformer.py:55-58]
+  // 6. mlp[2] + norm2 + residual -> cat[:, 0:C] (and x_f32 after the last layer)   [transformer.py:55-58]
+  // The residual stream lives in the fp16 planes (x = hi + lo, exact to 2^-22 relative): no fp32 master copy is read
+  // or written between layers.
   {
     using Epi = EpiLayerNorm<BN>;
     Planes A{w.h_hi + x_base * ldc, w.h_lo + x_base * ldc, ldc, 0};
     Planes B{lw.w2_hi, lw.w2_lo, 2 * C, 0};
-    float* xf = st.x_f32 + x_base * C;
-    typename Epi::Params ep{lw.ln2_g, lw.ln2_b, 1e-5f, xf, C, xf, C,
+    float* xf = write_f32 ? st.x_f32 + x_base * C : nullptr;
+    typename Epi::Params ep{lw.ln2_g, lw.ln2_b, 1e-5f, nullptr, 0, cat_hi + x_base * ldc, cat_lo + x_base * ldc,
+                            static_cast<int>(ldc), xf, C,
                             static_cast<__half*>(st.cat_hi) + x_base * ldc,
                             static_cast<__half*>(st.cat_lo) + x_base * ldc, static_cast<int>(ldc), 0, lw.s_2};
     LB_TRY((launch_gemm<BN, Epi>(TAG_MLP2_LN, A, B, 1, static_cast<int>(x_rows), C, 2 * C, 0, ep, stream)));
@@ -571,6 +677,11 @@ extern "C" {
 
 int lb_version(void) { return 100; }
 int lb_block_k(void) { return kBlockK; }
+int lb_conv_layout(int cin, int* cin_blocks, int* rem_channels) {
+  if (!cin_blocks || !rem_channels || cin <= 0) return fail("lb_conv_layout: bad arguments");
+  conv_layout(cin, cin_blocks, rem_channels);
+  return 0;
+}
 const char* lb_last_error(void) { return g_err; }
 long long lb_launch_count(void) { return g_launches.load(); }
 
@@ -731,7 +842,8 @@ int lb_split_planes(const float* x, long rows, int cols, int ld_x, void* hi, voi
                     void* stream) {
   if (rows <= 0 || cols <= 0) return 0;
   int sms;
-  LB_TRY(bind_device_of(x));
+  DeviceGuard dev_guard;
+  LB_TRY(dev_guard.bind(x));
   LB_TRY(device_check(&sms));
   const long total = rows * cols;
   const int grid = static_cast<int>(total / 256 + 1 < 4096 ? total / 256 + 1 : 4096);
@@ -745,7 +857,8 @@ int lb_gemm_split(const void* a_hi, const void* a_lo, long lda, long a_batch_str
                   const void* b_lo, long ldb, long b_batch_stride, float* out, long ldo, long o_batch_stride,
                   int batches, int M, int N, int K, void* stream) {
   if (N % 32 != 0) return fail("lb_gemm_split: N must be a multiple of 32");
-  LB_TRY(bind_device_of(out));
+  DeviceGuard dev_guard;
+  LB_TRY(dev_guard.bind(out));
   if (batches > 1 && o_batch_stride != static_cast<long>(M) * ldo)
     return fail("lb_gemm_split: output batches must be densely stacked (o_batch_stride == M*ldo)");
   Planes A{a_hi, a_lo, lda, batches > 1 ? a_batch_stride : 0};
@@ -765,7 +878,8 @@ int lb_coarse_prep(const float* feat, int nhwc, const float* pe, int n_img, int 
                    float* x_f32, void* cat_hi, void* cat_lo, void* stream) {
   int sms;
   if (n_img <= 0) return 0;
-  LB_TRY(bind_device_of(x_f32));
+  DeviceGuard dev_guard;
+  LB_TRY(dev_guard.bind(x_f32));
   LB_TRY(device_check(&sms));
   if (h > pe_h || w > pe_w) return fail("feature map %dx%d exceeds the position-encoding table %dx%d", h, w, pe_h, pe_w);
   if (n_img <= 0) return 0;
@@ -780,7 +894,7 @@ size_t lb_transformer_workspace_bytes(int d_model, int nhead, int n_groups, int 
   Bump b{nullptr, 0};
   TfWs w;
   const long R = static_cast<long>(n_groups) * (group_rows0 + group_rows1);
-  carve_tf(b, w, d_model, nhead, R, n_groups, d_model / nhead == 32);
+  carve_tf(b, w, d_model, nhead, R, n_groups, d_model / nhead == 32, group_rows0 > group_rows1 ? group_rows0 : group_rows1);
   return b.off + 256;
 }
 
@@ -788,7 +902,8 @@ int lb_transformer_forward(const LbEncoderLayerWeights* layers, const int* kinds
                            int nhead, const LbTransformerState* st, void* ws, size_t ws_bytes, void* stream) {
   int sms;
   if (st->n_groups <= 0) return 0;
-  LB_TRY(bind_device_of(st->x_f32));
+  DeviceGuard dev_guard;
+  LB_TRY(dev_guard.bind(st->x_f32));
   LB_TRY(device_check(&sms));
   const int C = d_model, H = nhead;
   const bool coarse = (C == 256 && H == 8);
@@ -800,15 +915,17 @@ int lb_transformer_forward(const LbEncoderLayerWeights* layers, const int* kinds
   if (!ws) return fail("workspace pointer is null");
   Bump b{static_cast<uint8_t*>(ws), ws_bytes};
   TfWs w;
-  carve_tf(b, w, C, H, rows0 + rows1, st->n_groups, coarse);
+  carve_tf(b, w, C, H, rows0 + rows1, st->n_groups, coarse,
+           st->group_rows0 > st->group_rows1 ? st->group_rows0 : st->group_rows1);
   if (!b.ok) return fail("transformer workspace too small: need %zu bytes", lb_transformer_workspace_bytes(C, H, st->n_groups, st->group_rows0, st->group_rows1));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool same_groups = st->group_rows0 == st->group_rows1;
   for (int l = 0; l < n_layers; ++l) {
     const LbEncoderLayerWeights& lw = layers[l];
+    const bool last = l == n_layers - 1;   // the fp32 copy of the features is only written after the last layer
     auto pass = [&](long xb, long xr, int xg, long sb, long sr, int sg, int ng, bool self_pass) -> int {
-      return coarse ? tf_layer_pass<256>(lw, C, H, *st, w, xb, xr, xg, sb, sr, sg, ng, self_pass, s)
-                    : tf_layer_pass<128>(lw, C, H, *st, w, xb, xr, xg, sb, sr, sg, ng, self_pass, s);
+      return coarse ? tf_layer_pass<256>(lw, C, H, *st, w, xb, xr, xg, sb, sr, sg, ng, self_pass, last, s)
+                    : tf_layer_pass<128>(lw, C, H, *st, w, xb, xr, xg, sb, sr, sg, ng, self_pass, last, s);
     };
     if (kinds[l] == LB_LAYER_SELF) {
       // feat0 = layer(feat0, feat0); feat1 = layer(feat1, feat1)  [transformer.py:93-94]; same weights,
@@ -842,7 +959,8 @@ int lb_backbone_forward(const LbBackboneWeights* w, const float* images, int N, 
                         float* feat_f_nhwc, void* ws, size_t ws_bytes, void* stream) {
   int sms;
   if (N <= 0) return 0;
-  LB_TRY(bind_device_of(images));
+  DeviceGuard dev_guard;
+  LB_TRY(dev_guard.bind(images));
   LB_TRY(device_check(&sms));
   if (H % 8 != 0 || W % 8 != 0) return fail("image size %dx%d must be divisible by 8", H, W);
   if (!ws) return fail("workspace pointer is null");
@@ -949,7 +1067,8 @@ size_t lb_coarse_match_workspace_bytes(int n_pairs, int L, int S) {
 
 int lb_coarse_match(const LbCoarseMatchArgs* a, void* ws, size_t ws_bytes, void* stream) {
   int sms;
-  LB_TRY(bind_device_of(a->count));
+  DeviceGuard dev_guard;
+  LB_TRY(dev_guard.bind(a->count));
   LB_TRY(device_check(&sms));
   const int n = a->n_pairs, L = a->L, S = a->S, C = a->C;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1145,7 +1264,8 @@ size_t lb_fine_preprocess_workspace_bytes(long M, int W, int Cf) {
 int lb_fine_preprocess(const LbFinePreprocessArgs* a, void* ws, size_t ws_bytes, void* stream) {
   int sms;
   if (a->M <= 0) return 0;
-  LB_TRY(bind_device_of(a->x_f32));
+  DeviceGuard dev_guard;
+  LB_TRY(dev_guard.bind(a->x_f32));
   LB_TRY(device_check(&sms));
   if (a->Cf != 128 || a->Cc > 256) return fail("fine preprocess built for Cf=128, Cc<=256 (got %d, %d)", a->Cf, a->Cc);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1191,7 +1311,8 @@ int lb_fine_preprocess(const LbFinePreprocessArgs* a, void* ws, size_t ws_bytes,
 int lb_fine_match(const LbFineMatchArgs* a, void* stream) {
   int sms;
   if (a->M <= 0) return 0;
-  LB_TRY(bind_device_of(a->expec_f));
+  DeviceGuard dev_guard;
+  LB_TRY(dev_guard.bind(a->expec_f));
   LB_TRY(device_check(&sms));
   if (a->W * a->W > 32) return fail("fine window %dx%d exceeds one warp", a->W, a->W);
   FineMatchParams p;

@@ -64,6 +64,23 @@ __device__ __forceinline__ void load_acc32(uint32_t tmem_acc, int col, float (&x
   for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
 }
 
+__device__ __forceinline__ void load_planes32(const __half* hp, const __half* lp, float (&x)[32]) {
+  const uint4* h4 = reinterpret_cast<const uint4*>(hp);
+  const uint4* l4 = reinterpret_cast<const uint4*>(lp);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 a = h4[j], b = l4[j];
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&aw[k]));
+      const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&bw[k]));
+      x[j * 8 + 2 * k] = fh.x + fl.x;
+      x[j * 8 + 2 * k + 1] = fh.y + fl.y;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // out[row, col] = act(acc) * rowmask[row];  act = elu(x)+1 for col < elu_cols, identity otherwise.
 // Covers q/k/v projection + feature map + padding mask of LinearAttention
@@ -109,6 +126,218 @@ struct EpiActStore {
   }
 };
 
+
+// ------------------------------------------------------------------------------------------------
+// Linear attention fused into the projections (reference linear_attention.py:31-46).
+// The fp32 q / k / v tensors of the reference never reach HBM.
+//
+// EpiKv: epilogue of the k|v projection.  The B operand is the row-permuted weight [Wk(heads 4t..4t+3) ; Wv(same
+// heads)] so that n-tile t holds, for kHeads = BLOCK_N / (2 D) heads, K in columns [0, BLOCK_N/2) and V in columns
+// [BLOCK_N/2, BLOCK_N).  K = elu(k)+1 and the padding mask are applied (linear_attention.py:32-39); per head the
+// 128-row tile contributes
+//     KV[d][v] += sum_r K[r][d] V[r][v],   Ksum[d] += sum_r K[r][d]                          (:43-44)
+// which is evaluated on the CUDA cores from a shared-memory staging of the head's K and V columns (thread = 2 d x 8 v
+// outputs over a quarter of the rows, then a 4-way merge) and written as ONE partial per (group, row tile, head):
+// part[batch][m_tile][head][D*D + D]; kv_tile_merge_kernel sums the row tiles in fixed order (bit-reproducible).
+template <int BLOCK_N, int D>
+struct EpiKv {
+  static_assert(D == 32 && BLOCK_N == 256, "built for the coarse transformer (d_model 256, 8 heads)");
+  struct Params {
+    const uint8_t* rowmask;  // optional [batches*M] (1 = valid)
+    float acc_scale;
+    float* part;             // [batches][m_tiles][H][D*D + D]
+    int H;
+  };
+  static constexpr int kHeads = BLOCK_N / (2 * D);      // heads per n-tile (4)
+  static constexpr int kPer = D * D + D;
+  static constexpr int kSmemBytes = 2 * 128 * D * 4;    // K and V staging (aliased by the 4-way merge buffer)
+  static_assert(4 * kPer * 4 <= kSmemBytes, "merge buffer must fit in the staging area");
+  const Params& p;
+  const GemmShape& s;
+  float* sK;   // [128][D], float4 index q of row r stored at q ^ (r & 7)
+  float* sV;
+  float* red;  // [4][kPer] aliasing sK/sV
+  __device__ EpiKv(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_) {
+    sK = reinterpret_cast<float*>(smem);
+    sV = sK + 128 * D;
+    red = sK;
+  }
+  __device__ void item_begin(int, int, int) {}
+  __device__ void item_end(int, int, int) {}
+  __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
+    const int t = epi_tid();
+    const int row = epi_row();
+    const int half = epi_half();
+    const int r = m0 + row;
+    const bool row_ok = r < s.M;
+    float mk = row_ok ? 1.f : 0.f;
+    if (row_ok && p.rowmask) mk = p.rowmask[static_cast<long>(batch) * s.M + r] ? 1.f : 0.f;
+    // compute-phase mapping: row quarter g, d pair, v octet
+    const int g = t >> 6, lt = t & 63, d2 = lt >> 2, v8 = lt & 3;
+    const int head0 = (n0 / BLOCK_N) * kHeads;
+#pragma unroll 1
+    for (int j = 0; j < kHeads; ++j) {
+      {  // stage this head's K (column half 0) / V (column half 1) columns of my row
+        float x[32];
+        load_acc32(tmem_acc, (half * kHeads + j) * 32, x);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] *= p.acc_scale;
+        if (half == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = x[i] > 0.f ? x[i] + 1.f : expf(x[i]);
+        }
+        float* dst = (half == 0 ? sK : sV) + row * D;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(dst + ((q ^ (row & 7)) << 2)) =
+              make_float4(x[4 * q] * mk, x[4 * q + 1] * mk, x[4 * q + 2] * mk, x[4 * q + 3] * mk);
+      }
+      epi_bar_sync();
+      float acc0[8], acc1[8], ks0 = 0.f, ks1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc0[i] = 0.f;
+        acc1[i] = 0.f;
+      }
+#pragma unroll 4
+      for (int rr = g * 32; rr < g * 32 + 32; ++rr) {
+        const int sw = rr & 7;
+        const float2 k2 = *reinterpret_cast<const float2*>(sK + rr * D + (((d2 >> 1) ^ sw) << 2) + ((d2 & 1) << 1));
+        const float4 va = *reinterpret_cast<const float4*>(sV + rr * D + (((2 * v8) ^ sw) << 2));
+        const float4 vb = *reinterpret_cast<const float4*>(sV + rr * D + (((2 * v8 + 1) ^ sw) << 2));
+        acc0[0] = fmaf(k2.x, va.x, acc0[0]); acc0[1] = fmaf(k2.x, va.y, acc0[1]);
+        acc0[2] = fmaf(k2.x, va.z, acc0[2]); acc0[3] = fmaf(k2.x, va.w, acc0[3]);
+        acc0[4] = fmaf(k2.x, vb.x, acc0[4]); acc0[5] = fmaf(k2.x, vb.y, acc0[5]);
+        acc0[6] = fmaf(k2.x, vb.z, acc0[6]); acc0[7] = fmaf(k2.x, vb.w, acc0[7]);
+        acc1[0] = fmaf(k2.y, va.x, acc1[0]); acc1[1] = fmaf(k2.y, va.y, acc1[1]);
+        acc1[2] = fmaf(k2.y, va.z, acc1[2]); acc1[3] = fmaf(k2.y, va.w, acc1[3]);
+        acc1[4] = fmaf(k2.y, vb.x, acc1[4]); acc1[5] = fmaf(k2.y, vb.y, acc1[5]);
+        acc1[6] = fmaf(k2.y, vb.z, acc1[6]); acc1[7] = fmaf(k2.y, vb.w, acc1[7]);
+        ks0 += k2.x;
+        ks1 += k2.y;
+      }
+      epi_bar_sync();   // everyone is done reading the staging area: it becomes the merge buffer
+      {
+        float* rg = red + g * kPer;
+        const int da = 2 * d2, db = 2 * d2 + 1;
+        *reinterpret_cast<float4*>(rg + da * D + (((2 * v8) ^ (da & 7)) << 2)) = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
+        *reinterpret_cast<float4*>(rg + da * D + (((2 * v8 + 1) ^ (da & 7)) << 2)) = make_float4(acc0[4], acc0[5], acc0[6], acc0[7]);
+        *reinterpret_cast<float4*>(rg + db * D + (((2 * v8) ^ (db & 7)) << 2)) = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
+        *reinterpret_cast<float4*>(rg + db * D + (((2 * v8 + 1) ^ (db & 7)) << 2)) = make_float4(acc1[4], acc1[5], acc1[6], acc1[7]);
+        if (v8 == 0) {
+          rg[D * D + da] = ks0;
+          rg[D * D + db] = ks1;
+        }
+      }
+      epi_bar_sync();
+      {
+        float* out = p.part + ((static_cast<long>(batch) * s.m_tiles + m0 / kBlockM) * p.H + head0 + j) * kPer;
+        for (int e = t; e < kPer; e += kEpiThreads) {
+          int src = e;
+          if (e < D * D) {
+            const int d = e / D, v = e - d * D;
+            src = d * D + ((((v >> 2) ^ (d & 7)) << 2) | (v & 3));
+          }
+          out[e] = (red[src] + red[kPer + src]) + (red[2 * kPer + src] + red[3 * kPer + src]);
+        }
+      }
+      epi_bar_sync();   // the merge buffer is the next head's staging area
+    }
+  }
+};
+
+// EpiAttn: epilogue of the q projection.  Q = elu(q)+1 (masked), then for the head that owns each 32-column group
+//     out[r, h, :] = (Q[r,h,:] . KV[g,h]) / (Q[r,h,:] . Ksum[g,h] + eps)                    (linear_attention.py:44-46)
+// with KV / Ksum of the row's group (batch) staged in shared memory, written as fp16 planes = the A operand of the
+// merge projection.  Requires N == BLOCK_N == H * D (one n-tile) and a batched launch (batch = group).
+template <int BLOCK_N, int D>
+struct EpiAttn {
+  static_assert(D == 32 && BLOCK_N == 256, "built for the coarse transformer (d_model 256, 8 heads)");
+  struct Params {
+    const uint8_t* rowmask;  // optional [batches*M]
+    float acc_scale;
+    const float* kv;         // [batches][H][D*D + D]
+    float eps;
+    __half* att_hi;          // [batches*M, ld]
+    __half* att_lo;
+    int ld;
+  };
+  static constexpr int kH = BLOCK_N / D;
+  static constexpr int kPer = D * D + D;
+  static constexpr int kSmemBytes = kH * kPer * 4;
+  const Params& p;
+  const GemmShape& s;
+  float* sKV;
+  int cur_batch;
+  __device__ EpiAttn(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_), cur_batch(-1) {
+    sKV = reinterpret_cast<float*>(smem);
+  }
+  __device__ void item_begin(int batch, int, int) {
+    if (batch != cur_batch) {   // uniform over the 256 epilogue threads
+      epi_bar_sync();           // nobody still reads the previous group's matrices
+      const float4* src = reinterpret_cast<const float4*>(p.kv + static_cast<long>(batch) * kH * kPer);
+      float4* dst = reinterpret_cast<float4*>(sKV);
+      for (int i = epi_tid(); i < kH * kPer / 4; i += kEpiThreads) dst[i] = src[i];
+      epi_bar_sync();
+      cur_batch = batch;
+    }
+  }
+  __device__ void item_end(int, int, int) {}
+  __device__ void tile(uint32_t tmem_acc, int batch, int m0, int) {
+    const int r = m0 + epi_row();
+    const bool row_ok = r < s.M;
+    const long grow = static_cast<long>(batch) * s.M + r;
+    float mk = 1.f;
+    if (row_ok && p.rowmask) mk = p.rowmask[grow] ? 1.f : 0.f;
+    const int c_begin = epi_half() * (BLOCK_N / 64);
+#pragma unroll 1
+    for (int c = c_begin; c < c_begin + BLOCK_N / 64; ++c) {
+      float q[32];
+      load_acc32(tmem_acc, c * 32, q);
+      const float* kvh = sKV + c * kPer;   // head = column group
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float x = q[j] * p.acc_scale;
+        q[j] = (x > 0.f ? x + 1.f : expf(x)) * mk;
+      }
+      float zden = p.eps;
+#pragma unroll
+      for (int d = 0; d < D; ++d) zden = fmaf(q[d], kvh[D * D + d], zden);
+      const float z = 1.f / zden;
+      __half* hp = p.att_hi + grow * p.ld + c * 32;
+      __half* lp = p.att_lo + grow * p.ld + c * 32;
+#pragma unroll
+      for (int v8 = 0; v8 < D; v8 += 8) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float4 a = *reinterpret_cast<const float4*>(&kvh[d * D + v8]);
+          const float4 b = *reinterpret_cast<const float4*>(&kvh[d * D + v8 + 4]);
+          o[0] = fmaf(q[d], a.x, o[0]); o[1] = fmaf(q[d], a.y, o[1]);
+          o[2] = fmaf(q[d], a.z, o[2]); o[3] = fmaf(q[d], a.w, o[3]);
+          o[4] = fmaf(q[d], b.x, o[4]); o[5] = fmaf(q[d], b.y, o[5]);
+          o[6] = fmaf(q[d], b.z, o[6]); o[7] = fmaf(q[d], b.w, o[7]);
+        }
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __half h0, l0, h1, l1;
+          split_f16(o[2 * j] * z, h0, l0);
+          split_f16(o[2 * j + 1] * z, h1, l1);
+          hw[j] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
+          lw[j] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
+        }
+        if (row_ok) {
+          *reinterpret_cast<uint4*>(hp + v8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(lp + v8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+      }
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 // y = LayerNorm(acc) * gamma + beta (+ residual) over the full row (requires N == BLOCK_N).
 // Covers merge+norm1 and mlp[2]+norm2+residual of LoFTREncoderLayer (reference transformer.py:51-58).
@@ -118,8 +347,11 @@ struct EpiLayerNorm {
     const float* gamma;
     const float* beta;
     float eps;
-    const float* residual;  // optional [rows, ld_res]
+    const float* residual;  // optional fp32 residual [rows, ld_res]
     int ld_res;
+    const __half* res_hi;   // optional residual as fp16 planes [rows, ld_res_pl] (x = hi + lo, exact to 2^-22): the
+    const __half* res_lo;   // residual stream then needs no fp32 master copy between layers
+    int ld_res_pl;
     float* out_f32;         // optional [rows, ld_f32]
     int ld_f32;
     __half* out_hi;         // optional planes [rows, ld_pl], written at column offset pl_col0
@@ -199,6 +431,12 @@ struct EpiLayerNorm {
             x[4 * j + 2] += t.z;
             x[4 * j + 3] += t.w;
           }
+        }
+        if (p.res_hi) {
+          float r[32];
+          load_planes32(p.res_hi + grow * p.ld_res_pl + c * 32, p.res_lo + grow * p.ld_res_pl + c * 32, r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] += r[j];
         }
         if (p.out_f32) store_f32x32(p.out_f32 + grow * p.ld_f32 + c * 32, x);
         if (p.out_hi) {
@@ -285,23 +523,6 @@ struct EpiPlanes {
 //                                            align_corners=True) (:107-113)
 //   y = relu / leaky_relu(0.01) / identity
 // written as NHWC fp16 planes (the next convolution's A operand) and / or NHWC fp32.
-__device__ __forceinline__ void load_planes32(const __half* hp, const __half* lp, float (&x)[32]) {
-  const uint4* h4 = reinterpret_cast<const uint4*>(hp);
-  const uint4* l4 = reinterpret_cast<const uint4*>(lp);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint4 a = h4[j], b = l4[j];
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&aw[k]));
-      const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&bw[k]));
-      x[j * 8 + 2 * k] = fh.x + fl.x;
-      x[j * 8 + 2 * k + 1] = fh.y + fl.y;
-    }
-  }
-}
-
 template <int BLOCK_N>
 struct EpiConv {
   struct Params {
@@ -321,20 +542,23 @@ struct EpiConv {
     int f32_ld;
     int H_out, W_out, tiles_w;
   };
-  static constexpr int kSmemBytes = 2 * BLOCK_N * 4;
+  static constexpr int kChunks = (BLOCK_N + 31) / 32;        // 32-column groups of the tile (the last may be partial)
+  static constexpr int kChunksHalf0 = (kChunks + 1) / 2;     // column half 0 takes the first ones
+  static constexpr int kCols = kChunks * 32;
+  static constexpr int kSmemBytes = 2 * kCols * 4;
   const Params& p;
   const GemmShape& s;
   float* s_scale;
   float* s_shift;
   __device__ EpiConv(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_) {
     s_scale = reinterpret_cast<float*>(smem);
-    s_shift = s_scale + BLOCK_N;
+    s_shift = s_scale + kCols;
   }
   __device__ void item_begin(int, int, int) {}
   __device__ void item_end(int, int, int) {}
   __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
     const int t = epi_tid();
-    for (int j = t; j < BLOCK_N; j += kEpiThreads) {
+    for (int j = t; j < kCols; j += kEpiThreads) {
       const int c = n0 + j;
       s_scale[j] = c < s.N ? p.scale[c] : 0.f;
       s_shift[j] = c < s.N ? p.shift[c] : 0.f;
@@ -364,9 +588,10 @@ struct EpiConv {
       u10 = (base + static_cast<long>(y1) * p.up_w + x0) * p.up_ld;
       u11 = (base + static_cast<long>(y1) * p.up_w + x1) * p.up_ld;
     }
-    const int c_begin = epi_half() * (BLOCK_N / 64);
+    const int c_begin = epi_half() == 0 ? 0 : kChunksHalf0;
+    const int c_end = epi_half() == 0 ? kChunksHalf0 : kChunks;
 #pragma unroll 1
-    for (int c = c_begin; c < c_begin + BLOCK_N / 64; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
       const int col = n0 + c * 32;
       if (col >= s.N) break;
       float v[32];

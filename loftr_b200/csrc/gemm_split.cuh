@@ -43,13 +43,22 @@ __device__ __forceinline__ void epi_group_sync() { asm volatile("bar.sync 1, 256
 // patch shifted by the tap offset (out-of-image reads are zero-filled by TMA = the convolution's padding).
 constexpr int kConvTileH = 8;
 constexpr int kConvTileW = 16;
+// Channel remainder (Cin = 64*cin_blocks + r, 0 < r <= 16, e.g. 196 = 3*64 + 4): instead of a fourth, 94 % empty
+// 64-channel block per tap, the r channels of every tap travel as 16-channel boxes (32-byte swizzle rows, one K = 16
+// MMA step per tap); four taps share one pipeline stage ("remainder group").  K-steps per output for a 3x3 / Cin = 196
+// convolution: 9*3*4 + 9 = 117 instead of 9*4*4 = 144.
+constexpr int kRemChannels = 16;
+constexpr int kRemTapsPerStage = 4;
 struct ConvGeom {
   int enabled;     // 0: plain GEMM (3-D maps)
   int tiles_w;     // spatial tiles per tile row; m_tile = ty * tiles_w + tx
   int stride;      // 1 or 2 (also encoded as the map's element stride)
   int pad;
-  int taps_w;      // kernel width (taps = K / 64 / cin_blocks)
-  int cin_blocks;  // ceil(Cin / 64)
+  int taps_w;      // kernel width
+  int cin_blocks;  // full 64-channel blocks per tap
+  int taps;        // kernel taps (ksize^2)
+  int n_main;      // taps * cin_blocks k-blocks of 64 channels
+  int rem_groups;  // 0, or ceil(taps / 4) remainder groups that follow the main k-blocks
 };
 
 struct GemmShape {
@@ -69,6 +78,8 @@ struct GemmShape {
 __device__ __forceinline__ uint64_t umma_desc_k(uint32_t smem_addr) {
   return kBlockK == 64 ? umma_desc_k_sw128(smem_addr) : umma_desc_k_sw64(smem_addr);
 }
+// power of two >= x (TMEM allocations)
+constexpr uint32_t pow2_at_least(uint32_t x) { return x <= 32 ? 32 : x <= 64 ? 64 : x <= 128 ? 128 : x <= 256 ? 256 : 512; }
 
 // Shared-memory ring.  kPair (cta_group::2): a CTA stages its own 128 rows of A and only its HALF of the B tile.
 template <int BLOCK_N, bool kPair = false>
@@ -90,7 +101,9 @@ template <int BLOCK_N, bool kDual>
 struct AccLayout {
   static constexpr int kColsPerStage = kDual ? 2 * BLOCK_N : BLOCK_N;
   static constexpr int kStages = (2 * kColsPerStage <= 512) ? 2 : 1;
-  static constexpr uint32_t kTmemCols = kStages * kColsPerStage;  // 256 or 512: a power of two
+  // the epilogues read whole 32-column groups: the last group of a stage may run up to 31 columns past it
+  static_assert(kStages * kColsPerStage + 31 <= 512 || BLOCK_N % 32 == 0, "accumulator layout exceeds TMEM");
+  static constexpr uint32_t kTmemCols = pow2_at_least(kStages * kColsPerStage);
 };
 
 // Execution modes (kMode):
@@ -116,6 +129,8 @@ template <int BLOCK_N, class Epi, bool kDual = false, int kMode = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                  const __grid_constant__ CUtensorMap tm_ar_hi, const __grid_constant__ CUtensorMap tm_ar_lo,
+                  const __grid_constant__ CUtensorMap tm_br_hi, const __grid_constant__ CUtensorMap tm_br_lo,
                   const GemmShape shape, const typename Epi::Params epi_params) {
   constexpr bool kPair = kMode == 2;
   constexpr bool kMcast = kMode == 1;
@@ -169,7 +184,13 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_kb = shape.K / kBlockK;
+  // k-blocks of one output tile: K / 64 full blocks (+ the channel-remainder groups of a convolution)
+  const int num_kb = shape.conv.enabled ? shape.conv.n_main + shape.conv.rem_groups : shape.K / kBlockK;
+  constexpr int kTapBytes = S::kStageBytes / kRemTapsPerStage;   // one tap of a remainder group: A_hi A_lo B_hi B_lo
+  constexpr int kRemATile = kBlockM * kRemChannels * 2;           // 4 KB
+  constexpr int kRemBTile = S::kBTile / (kBlockK / kRemChannels);
+  static_assert(kBlockK != 64 || (kTapBytes == 2 * kRemATile + 2 * kRemBTile && kTapBytes % 256 == 0 &&
+                                  kRemBTile % 256 == 0), "remainder group layout");
   // Work items.  Single CTA: (batch, m_tile, chunk).  Cluster: (batch, m_tile group, chunk); CTA rank r of the
   // cluster takes m_tile = group * kCluster + r (a phantom tile past the end is loaded/multiplied but not emitted).
   const int m_groups = (shape.m_tiles + kCluster - 1) / kCluster;
@@ -194,15 +215,53 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = ring + stage * S::kStageBytes;
             uint64_t* fb = &full_bar[stage];
+            const bool rem_group = shape.conv.enabled && kb >= shape.conv.n_main;
+            int rem_t0 = 0, rem_nt = 0;
+            uint32_t stage_tx = S::kStageBytes;
+            if (rem_group) {
+              rem_t0 = (kb - shape.conv.n_main) * kRemTapsPerStage;
+              rem_nt = min(kRemTapsPerStage, shape.conv.taps - rem_t0);
+              stage_tx = static_cast<uint32_t>(rem_nt) * kTapBytes;
+            }
             if (kPair) {
               // both CTAs' bytes are credited to the leader's barrier
               if (leader) {
-                mbar_arrive_expect_tx(fb, 2 * S::kStageBytes);
+                mbar_arrive_expect_tx(fb, 2 * stage_tx);
               } else {
                 mbar_arrive_remote(fb, 0);
               }
             } else {
-              mbar_arrive_expect_tx(fb, S::kStageBytes);
+              mbar_arrive_expect_tx(fb, stage_tx);
+            }
+            if (rem_group) {
+              // ---- channel remainder: up to four taps, each a 16-channel box of A (hi, lo) and of the weights
+              const ConvGeom& g = shape.conv;
+              const int ty = mt / g.tiles_w, tx = mt - ty * g.tiles_w;
+              for (int t = 0; t < rem_nt; ++t) {
+                const int tap = rem_t0 + t;
+                const int ky = tap / g.taps_w, kx = tap - ky * g.taps_w;
+                const int x = tx * kConvTileW * g.stride + kx - g.pad;
+                const int y = ty * kConvTileH * g.stride + ky - g.pad;
+                uint8_t* base = st + t * kTapBytes;
+                const int c0 = g.cin_blocks * kBlockK;
+                if (kPair) {
+                  const int row0 = nt * BLOCK_N + crank * (BLOCK_N / 2);
+                  tma_load_4d_2sm(base, &tm_ar_hi, fb, c0, x, y, batch);
+                  tma_load_4d_2sm(base + kRemATile, &tm_ar_lo, fb, c0, x, y, batch);
+                  tma_load_3d_2sm(base + 2 * kRemATile, &tm_br_hi, fb, tap * kRemChannels, row0, 0);
+                  tma_load_3d_2sm(base + 2 * kRemATile + kRemBTile, &tm_br_lo, fb, tap * kRemChannels, row0, 0);
+                } else {
+                  tma_load_4d(base, &tm_ar_hi, fb, c0, x, y, batch);
+                  tma_load_4d(base + kRemATile, &tm_ar_lo, fb, c0, x, y, batch);
+                  tma_load_3d(base + 2 * kRemATile, &tm_br_hi, fb, tap * kRemChannels, nt * BLOCK_N, 0);
+                  tma_load_3d(base + 2 * kRemATile + kRemBTile, &tm_br_lo, fb, tap * kRemChannels, nt * BLOCK_N, 0);
+                }
+              }
+              if (++stage == S::kStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+              continue;
             }
             // ---- A: this CTA's 128 rows (or 8 x 16 pixel patch shifted by the tap)
             if (shape.conv.enabled) {
@@ -274,6 +333,39 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t st = smem_u32(ring + stage * S::kStageBytes);
+            if (shape.conv.enabled && kb >= shape.conv.n_main) {
+              // remainder group: one K = 16 step per tap, 32-byte swizzle rows (kb > 0 here: always accumulate)
+              const int rem_t0 = (kb - shape.conv.n_main) * kRemTapsPerStage;
+              const int rem_nt = min(kRemTapsPerStage, shape.conv.taps - rem_t0);
+              for (int t = 0; t < rem_nt; ++t) {
+                const uint32_t base = st + t * kTapBytes;
+                const uint64_t ra_hi = umma_desc_k_sw32(base);
+                const uint64_t ra_lo = umma_desc_k_sw32(base + kRemATile);
+                const uint64_t rb_hi = umma_desc_k_sw32(base + 2 * kRemATile);
+                const uint64_t rb_lo = umma_desc_k_sw32(base + 2 * kRemATile + kRemBTile);
+                if (kPair) {
+                  umma_f16_2sm(d_tmem, ra_hi, rb_hi, idesc, 1u);
+                  umma_f16_2sm(d_corr, ra_hi, rb_lo, idesc, 1u);
+                  umma_f16_2sm(d_corr, ra_lo, rb_hi, idesc, 1u);
+                } else {
+                  umma_f16(d_tmem, ra_hi, rb_hi, idesc, 1u);
+                  umma_f16(d_corr, ra_hi, rb_lo, idesc, 1u);
+                  umma_f16(d_corr, ra_lo, rb_hi, idesc, 1u);
+                }
+              }
+              if (kPair) {
+                umma_commit_2sm_mc(&empty_bar[stage], kMcMask);
+              } else if (kMcast) {
+                umma_commit_mc(&empty_bar[stage], kMcMask);
+              } else {
+                umma_commit(&empty_bar[stage]);
+              }
+              if (++stage == S::kStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+              continue;
+            }
             const uint64_t da_hi = umma_desc_k(st);
             const uint64_t da_lo = umma_desc_k(st + S::kATile);
             const uint64_t db_hi = umma_desc_k(st + 2 * S::kATile);

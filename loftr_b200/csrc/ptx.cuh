@@ -283,6 +283,17 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
   return d;
 }
 
+// Rows of 32 bytes (16 fp16) with the 32-byte swizzle: 8-row groups are 256 bytes apart, layout type 6.
+__device__ __forceinline__ uint64_t umma_desc_k_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;
+  return d;
+}
+
 // Instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=f16 (0), both K-major,
 // N>>3 at bit 17, M>>4 at bit 24.
 __host__ __device__ constexpr uint32_t umma_idesc_f16_f32(uint32_t M, uint32_t N) {

@@ -248,6 +248,20 @@ __global__ void kv_merge_kernel(const float* __restrict__ part, int nsplit, int 
   kv[i] = s;
 }
 
+// Sum of the per-row-tile partials written by the EpiKv epilogue: part [groups][m_tiles][H*per] -> kv [groups][H*per]
+// (fixed order over the row tiles: bit-reproducible).
+__global__ void kv_tile_merge_kernel(const float* __restrict__ part, int m_tiles, int hper, float* __restrict__ kv,
+                                     long total) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const long g = i / hper;
+  const int e = static_cast<int>(i - g * hper);
+  const float* src = part + g * m_tiles * hper + e;
+  float acc = 0.f;
+  for (int k = 0; k < m_tiles; ++k) acc += src[static_cast<long>(k) * hper];
+  kv[i] = acc;
+}
+
 // Window variant for the fine transformer (group = one 5x5 window = 25 rows, D = 16, H = 8):
 // one block per window, all heads; writes kv directly.
 template <int D, int H>

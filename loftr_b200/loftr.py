@@ -2,10 +2,19 @@
 
 Same constructor argument (the lower-case config dict), same sub-module and parameter names (so
 `state_dict`s and released checkpoints round-trip), same `forward(data) -> None` contract that
-mutates `data` with the reference's output keys.  The ResNet-FPN backbone runs in PyTorch; everything
-after it (position encoding, coarse transformer, coarse matching, fine windows, fine transformer, fine
-matching) runs in the hand-written sm_100a kernels behind the C ABI of include/loftr_b200.h.
+mutates `data` with the reference's output keys.  Everything runs in the hand-written sm_100a kernels behind the
+C ABI of include/loftr_b200.h: the ResNet-FPN backbone as implicit-GEMM convolutions on the tensor cores
+(`backbone_impl="b200"`, the default for the shipped ResNetFPN_8_2 shape; `"torch"` keeps the PyTorch/cuDNN fp32
+forward, which is ~9x closer to fp64 -- DESIGN.md §9), then position encoding, coarse transformer, coarse
+matching, fine windows, fine transformer and fine matching.
 There is no fallback path: without the built library / a B200 the forward raises.
+
+Packed-weight caches.  The kernels read fp16 hi/lo planes packed lazily from the parameters.  The caches are
+rebuilt when a parameter is replaced or modified through autograd-visible in-place ops (`_version` / `data_ptr`
+change) and are dropped by `load_state_dict`, `.to()/.cuda()/.float()` (`_apply`) and `invalidate_packed()`.
+Writes through `.data` (`p.data.copy_(w)`, EMA swaps, `m.weight.data.normal_()`) change neither `_version` nor
+`data_ptr`: call `model.invalidate_packed()` after them.  The caches never enter `copy.deepcopy` / `pickle` /
+`torch.save(model)` state.
 """
 from __future__ import annotations
 
@@ -21,8 +30,37 @@ from .backbone import build_backbone
 _KIND = {"self": _lib.LAYER_SELF, "cross": _lib.LAYER_CROSS}
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(ref=None):
+    """cudaStream_t of torch's current stream ON THE DEVICE THAT OWNS `ref` (a tensor or torch.device); the library
+    binds itself to the device of the buffers it is given, so the stream handle must belong to that device too."""
+    dev = ref.device if torch.is_tensor(ref) else ref
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+class _PackedCacheMixin:
+    """Keeps the ctypes / device-plane weight caches out of deepcopy / pickle state and drops them whenever the
+    parameters are re-materialised (`_apply`: .to / .cuda / .float / .half) or re-loaded."""
+    _CACHE_ATTRS = ("_packed", "_packed_key")
+
+    def invalidate_packed(self):
+        for a in self._CACHE_ATTRS:
+            if a in self.__dict__:
+                self.__dict__[a] = None
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        for a in self._CACHE_ATTRS:
+            if a in d:
+                d[a] = None
+        return d
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate_packed()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.invalidate_packed()
+        return super()._load_from_state_dict(*args, **kwargs)
 
 
 def _require_cuda(t: torch.Tensor, name: str):
@@ -54,7 +92,7 @@ def split_planes(x: torch.Tensor, hi: torch.Tensor | None = None, lo: torch.Tens
         lo = torch.empty(rows, cols, dtype=torch.float16, device=x.device)
     lib = _lib.load()
     _lib.check(lib.lb_split_planes(x.data_ptr(), rows, cols, x.stride(0), hi.data_ptr(), lo.data_ptr(), hi.stride(0),
-                                   col0, _stream()))
+                                   col0, _stream(x)))
     return hi, lo
 
 
@@ -67,6 +105,13 @@ class TensorCoreBackbone:
         self.m = torch_backbone
         self._packed = None
         self._key = None
+
+    def invalidate_packed(self):
+        self._packed = None
+        self._key = None
+
+    def __getstate__(self):   # the cache holds ctypes structures with device pointers: never copied / pickled
+        return {"m": self.m, "_packed": None, "_key": None}
 
     @staticmethod
     def supported(torch_backbone) -> bool:
@@ -85,16 +130,31 @@ class TensorCoreBackbone:
     def _conv(self, conv, bn, keep):
         w = conv.weight.detach().float()                      # [cout, cin, k, k]
         cout, cin, k, _ = w.shape
-        bk = _lib.load().lb_block_k()
-        cb = -(-cin // bk) * bk
-        wp = torch.zeros(cout, k * k, cb, device=w.device)
-        wp[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, k * k, cin)   # tap-major, channels padded per tap
-        hi, lo, acc_scale = split_weight(wp.reshape(cout, k * k * cb))
+        lib = _lib.load()
+        bk = lib.lb_block_k()
+        cbl, rem = C.c_int(), C.c_int()
+        _lib.check(lib.lb_conv_layout(cin, C.byref(cbl), C.byref(rem)))
+        cmain = cbl.value * bk                                # channels per tap in the main planes
+        wt = w.permute(0, 2, 3, 1).reshape(cout, k * k, cin)  # tap-major
+        wp = torch.zeros(cout, k * k, cmain, device=w.device)
+        wp[:, :, :min(cin, cmain)] = wt[:, :, :cmain]
+        planes = [wp.reshape(cout, k * k * cmain)]
+        if rem.value:                                         # channels cmain .. cin-1 of every tap, padded to 16
+            wr = torch.zeros(cout, k * k, 16, device=w.device)
+            wr[:, :, :rem.value] = wt[:, :, cmain:]
+            planes.append(wr.reshape(cout, k * k * 16))
+        # one power-of-two scale for both plane sets (they feed the same accumulator)
+        hi, lo, acc_scale = split_weight(torch.cat(planes, 1))
+        nmain = k * k * cmain
+        hi_m, lo_m = hi[:, :nmain].contiguous(), lo[:, :nmain].contiguous()
+        hi_r = lo_r = None
+        if rem.value:
+            hi_r, lo_r = hi[:, nmain:].contiguous(), lo[:, nmain:].contiguous()
         scale, shift = self._fold(bn, cout, w.device)
         scale = (scale * acc_scale).contiguous()   # y = acc * (2^-e * bn_scale) + bn_shift
-        keep += [hi, lo, scale, shift]
-        return _lib.LbConvWeights(hi.data_ptr(), lo.data_ptr(), scale.data_ptr(), shift.data_ptr(), cin, cout, k,
-                                  conv.stride[0])
+        keep += [hi_m, lo_m, hi_r, lo_r, scale, shift]
+        return _lib.LbConvWeights(hi_m.data_ptr(), lo_m.data_ptr(), _lib.ptr(hi_r), _lib.ptr(lo_r), scale.data_ptr(),
+                                  shift.data_ptr(), cin, cout, k, conv.stride[0])
 
     def _pack(self):
         m = self.m
@@ -140,7 +200,7 @@ class TensorCoreBackbone:
         nbytes = lib.lb_backbone_workspace_bytes(C.byref(w), n, h, wd)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=images.device)
         _lib.check(lib.lb_backbone_forward(C.byref(w), images.data_ptr(), n, h, wd, feat_c.data_ptr(),
-                                           feat_f.data_ptr(), ws.data_ptr(), nbytes, _stream()))
+                                           feat_f.data_ptr(), ws.data_ptr(), nbytes, _stream(images)))
         return feat_c, feat_f
 
 
@@ -199,7 +259,7 @@ class _TokenState:
         self.cat_lo = torch.empty(rows, 2 * c, dtype=torch.float16, device=device)
 
 
-class LocalFeatureTransformer(nn.Module):
+class LocalFeatureTransformer(_PackedCacheMixin, nn.Module):
     """Interleaved self/cross linear-attention encoder (reference transformer.py:61-101)."""
 
     def __init__(self, config):
@@ -231,10 +291,19 @@ class LocalFeatureTransformer(nn.Module):
                 planes = [(h, l) for h, l, _ in scaled]
                 lns = [layer.norm1.weight, layer.norm1.bias, layer.norm2.weight, layer.norm2.bias]
                 lns = [t.detach().float().contiguous() for t in lns]
-                keep.append((planes, lns))
                 w = arr[i]
+                c, d = self.d_model, self.d_model // self.nhead
+                if d == 32 and c == 256:
+                    # fused k|v projection: k and v rows regrouped in blocks of 4 heads (128 rows)
+                    idx = torch.cat([torch.arange(c + blk * 128, c + blk * 128 + 128).repeat(1) if part == 0 else
+                                     torch.arange(2 * c + blk * 128, 2 * c + blk * 128 + 128)
+                                     for blk in range(c // 128) for part in (0, 1)]).to(planes[0][0].device)
+                    wkv = (planes[0][0][idx].contiguous(), planes[0][1][idx].contiguous())
+                    planes.append(wkv)
+                    w.wkv_hi, w.wkv_lo = wkv[0].data_ptr(), wkv[1].data_ptr()
+                keep.append((planes, lns))
                 (w.wqkv_hi, w.wqkv_lo), (w.wm_hi, w.wm_lo), (w.w1_hi, w.w1_lo), (w.w2_hi, w.w2_lo) = [
-                    (h.data_ptr(), l.data_ptr()) for h, l in planes]
+                    (h.data_ptr(), l.data_ptr()) for h, l in planes[:4]]
                 w.ln1_g, w.ln1_b, w.ln2_g, w.ln2_b = [t.data_ptr() for t in lns]
                 w.s_qkv, w.s_m, w.s_1, w.s_2 = [sc for _, _, sc in scaled]
         kinds = (C.c_int * len(self.layers))(*[_KIND[n] for n in self.layer_names])
@@ -251,7 +320,7 @@ class LocalFeatureTransformer(nn.Module):
         nbytes = lib.lb_transformer_workspace_bytes(self.d_model, self.nhead, n_groups, group_rows0, group_rows1)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=state.x.device)
         _lib.check(lib.lb_transformer_forward(arr, kinds, len(self.layers), self.d_model, self.nhead, C.byref(st),
-                                              ws.data_ptr(), nbytes, _stream()))
+                                              ws.data_ptr(), nbytes, _stream(state.x)))
 
     @torch.no_grad()
     def forward(self, feat0, feat1, mask0=None, mask1=None):
@@ -337,7 +406,7 @@ class CoarseMatching(nn.Module):
             a.conf_matrix = conf.data_ptr()
         nbytes = lib.lb_coarse_match_workspace_bytes(n, L, S)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _lib.check(lib.lb_coarse_match(C.byref(a), ws.data_ptr(), nbytes, _stream()))
+        _lib.check(lib.lb_coarse_match(C.byref(a), ws.data_ptr(), nbytes, _stream(hi)))
         m = int(count.item())  # the one host sync of the coarse stage (sizes the match list)
         if m > cap:
             raise RuntimeError(f"loftr_b200: {m} coarse matches exceed the buffer capacity {cap}")
@@ -366,7 +435,7 @@ class CoarseMatching(nn.Module):
         self.run(hi, lo, c, n, L, S, c, data, m0, m1)
 
 
-class FinePreprocess(nn.Module):
+class FinePreprocess(_PackedCacheMixin, nn.Module):
     """Window gather + coarse-feature merge (reference fine_preprocess.py:7-59)."""
 
     def __init__(self, config):
@@ -431,7 +500,7 @@ class FinePreprocess(nn.Module):
         a.x_f32, a.cat_hi, a.cat_lo = state.x.data_ptr(), state.cat_hi.data_ptr(), state.cat_lo.data_ptr()
         nbytes = lib.lb_fine_preprocess_workspace_bytes(m, W, cf)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _lib.check(lib.lb_fine_preprocess(C.byref(a), ws.data_ptr(), nbytes, _stream()))
+        _lib.check(lib.lb_fine_preprocess(C.byref(a), ws.data_ptr(), nbytes, _stream(feat_f0)))
         return state
 
     @torch.no_grad()
@@ -482,7 +551,7 @@ class FineMatching(nn.Module):
             a.scale1 = keep.data_ptr()
         a.b_ids, a.mkpts1_c = data["b_ids"].data_ptr(), mk1c.data_ptr()
         a.expec_f, a.mkpts1_f = expec.data_ptr(), mk1f.data_ptr()
-        _lib.check(lib.lb_fine_match(C.byref(a), _stream()))
+        _lib.check(lib.lb_fine_match(C.byref(a), _stream(f0)))
         data.update({"expec_f": expec, "mkpts0_f": data["mkpts0_c"], "mkpts1_f": mk1f})
 
 
@@ -495,6 +564,17 @@ class LoFTR(nn.Module):
         "b200" whenever the configured backbone is the supported ResNetFPN_8_2 shape.  Both are GPU paths."""
         super().__init__()
         self.config = config
+        # the kernels are built for the shipped shapes; anything else must fail here, not at the first forward
+        cc, fc = config["coarse"], config["fine"]
+        if (cc["d_model"], cc["nhead"]) != (256, 8):
+            raise ValueError(f"loftr_b200 builds the coarse transformer for d_model=256, nhead=8 (got {cc['d_model']}, "
+                             f"{cc['nhead']})")
+        if (fc["d_model"], fc["nhead"]) != (128, 8):
+            raise ValueError(f"loftr_b200 builds the fine transformer for d_model=128, nhead=8 (got {fc['d_model']}, "
+                             f"{fc['nhead']})")
+        if config["fine_window_size"] ** 2 > 32 or config["fine_window_size"] % 2 == 0:
+            raise ValueError("loftr_b200 builds fine windows of odd size with at most 32 cells (fine_window_size <= 5)")
+        self.expose_coarse_features = False   # True: forward also writes data['_feat_c0'/'_feat_c1'] (not reference keys)
         self.backbone = build_backbone(config)
         if backbone_impl == "auto":
             backbone_impl = "b200" if TensorCoreBackbone.supported(self.backbone) else "torch"
@@ -548,7 +628,7 @@ class LoFTR(nn.Module):
         L, S = h0 * w0, h1 * w1
         state = _TokenState(bs * L, bs * S, c, img0.device)
         pe = self.pos_encoding.pe[0]
-        st = _stream()
+        st = _stream(img0)
         for feat, h, w, row0 in ((feat_c0, h0, w0, 0), (feat_c1, h1, w1, bs * L)):
             feat = feat.float()
             feat = feat.permute(0, 2, 3, 1).contiguous() if nhwc else feat.contiguous()   # no copy in either case
@@ -580,12 +660,26 @@ class LoFTR(nn.Module):
 
         # 5. fine matching                                                             [loftr.py:75]
         self.fine_matching(f0u, f1u, data)
-        # the coarse features are exposed for callers that want them (not a reference key)
-        data["_feat_c0"], data["_feat_c1"] = state.x[: bs * L].view(bs, L, c), state.x[bs * L:].view(bs, S, c)
+        if self.expose_coarse_features:   # test / debugging tap, off by default: not a reference key
+            data["_feat_c0"], data["_feat_c1"] = state.x[: bs * L].view(bs, L, c), state.x[bs * L:].view(bs, S, c)
+
+    def invalidate_packed(self):
+        """Drop every packed-weight cache (fp16 hi/lo planes, folded BatchNorm): required after parameter writes
+        that PyTorch cannot see (`.data` mutation); implied by load_state_dict / .to() / .cuda() / .float()."""
+        for m in self.modules():
+            if m is not self and hasattr(m, "invalidate_packed"):
+                m.invalidate_packed()
+        if self._tc_backbone is not None:
+            self._tc_backbone.invalidate_packed()
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate_packed()
+        return super()._apply(fn, *args, **kwargs)
 
     def load_state_dict(self, state_dict, *args, **kwargs):
         """Accepts checkpoints saved from the Lightning wrapper ('matcher.' prefix; reference loftr.py:77-81)."""
         for k in list(state_dict.keys()):
             if k.startswith("matcher."):
                 state_dict[k.replace("matcher.", "", 1)] = state_dict.pop(k)
+        self.invalidate_packed()
         return super().load_state_dict(state_dict, *args, **kwargs)

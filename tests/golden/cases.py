@@ -119,3 +119,24 @@ def build_cm_inputs(case, C=256):
             m1[b, : case["valid1c"][b][0], : case["valid1c"][b][1]] = True
         out["mask0"], out["mask1"] = m0, m1
     return out
+
+
+# Full-size cases of the BASELINE.json configs (GPU parity tests `tests/test_engine_gpu.py`; their oracle outputs
+# can be precomputed on CPU with tools/precompute_oracle.py into the git-ignored tests/_oracle_cache/).
+BASELINE_CASES = {
+    "full": {"name": "full", "n": 1, "hw0": (480, 640), "hw1": (480, 640), "thr": 0.0, "images": "smooth"},
+    "b8": {"name": "b8", "n": 8, "hw0": (480, 640), "hw1": (480, 640), "thr": 0.0, "images": "smooth"},
+    "b8thr": {"name": "b8thr", "n": 8, "hw0": (480, 640), "hw1": (480, 640), "thr": 0.2, "images": "smooth"},
+    "b8ot": {"name": "b8ot", "n": 8, "hw0": (480, 640), "hw1": (480, 640), "thr": 0.0, "images": "smooth",
+             "match_type": "sinkhorn"},
+    "ot_full": {"name": "ot_full", "n": 1, "hw0": (480, 640), "hw1": (480, 640), "thr": 0.0, "images": "smooth",
+                "match_type": "sinkhorn"},
+    "outdoor": {"name": "outdoor", "n": 1, "hw0": (832, 832), "hw1": (832, 832), "thr": 0.0, "images": "smooth",
+                "valid0": [(832, 624)], "valid1": [(640, 832)], "scales": True},
+    "out4": {"name": "out4", "n": 4, "hw0": (832, 832), "hw1": (832, 832), "thr": 0.0, "images": "smooth",
+             "valid0": [(832, 624), (832, 832), (560, 832), (704, 768)],
+             "valid1": [(640, 832), (768, 832), (832, 832), (832, 616)], "scales": True},
+    "sweep240": {"name": "sweep", "n": 1, "hw0": (240, 320), "hw1": (240, 320), "thr": 0.0, "images": "smooth"},
+    "sweep720": {"name": "sweep", "n": 1, "hw0": (720, 960), "hw1": (720, 960), "thr": 0.0, "images": "smooth"},
+    "sweep960": {"name": "sweep", "n": 1, "hw0": (960, 1280), "hw1": (960, 1280), "thr": 0.0, "images": "smooth"},
+}

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import util
-from cases import CASES, CM_CASES, build_cfg, build_cm_inputs, build_inputs
+from cases import BASELINE_CASES, CASES, CM_CASES, build_cfg, build_cm_inputs, build_inputs
 from oracle import loftr_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -126,7 +126,9 @@ def test_coarse_matching_full_size_vs_oracle():
     mod(_t(f0), _t(f1), data)
     got = {k: data[k].cpu().numpy() for k in ["b_ids", "i_ids", "j_ids", "mconf", "mkpts0_c", "mkpts1_c"]}
     assert len(out["b_ids"]) > 1000
-    stats = util.compare_matches(got, out, None, conf_rtol=1e-3, px_tol=1e-3, min_overlap=0.995, label="full")
+    g64 = [util.near_tie_top2_f64(f0[b], f1[b], cfg) for b in range(n)]
+    gold = {"row_top2_f64": np.stack([g[0] for g in g64]), "col_top2_f64": np.stack([g[1] for g in g64])}
+    stats = util.compare_matches(got, out, gold, conf_rtol=1e-3, px_tol=1e-3, min_overlap=0.995, label="full")
     assert stats["n"] > 1000
 
 
@@ -178,6 +180,7 @@ def _run_engine(case):
     data = {k: _t(v) for k, v in inp.items()}
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    model.expose_coarse_features = True   # test tap: data['_feat_c0'/'_feat_c1']
     model(data)
     return model, data
 
@@ -193,31 +196,79 @@ def test_end_to_end_matches_reference_golden(case):
                                               "mkpts1_f", "expec_f"]}
     np.testing.assert_allclose(data["_feat_c0"].cpu().numpy()[:, ::7, ::5], gold["feat_c0_s"], rtol=1e-3, atol=1e-3)
     np.testing.assert_allclose(data["_feat_c1"].cpu().numpy()[:, ::7, ::5], gold["feat_c1_s"], rtol=1e-3, atol=1e-3)
-    stats = util.compare_matches(got, gold, gold, conf_rtol=1e-3, px_tol=0.5, min_overlap=0.97, label=case["name"])
+    stats = util.compare_matches(got, gold, gold, conf_rtol=1e-3, px_tol=0.5, min_overlap=0.995, label=case["name"])
     util.record("e2e_golden_" + case["name"], stats)
     m = len(gold["b_ids"])
     if m == 0:
         assert got["b_ids"].shape == (0,) and got["mkpts0_f"].shape == (0, 2) and got["expec_f"].shape == (0, 3)
         assert data["mkpts0_f"] is data["mkpts0_c"]
     else:
-        assert stats["n"] >= 0.97 * m
+        assert stats["n"] >= m - max(1, int(0.005 * m))
     assert got["mkpts1_f"].dtype == np.float32 and data["m_bids"].dtype == torch.int64
     assert data["gt_mask"].dtype == torch.bool and data["gt_mask"].shape[0] == len(got["b_ids"])
 
 
-def test_end_to_end_640x480_vs_oracle():
-    """Config 1/2 of BASELINE.json (640x480, indoor_ds) at thr 0: engine vs oracle on the SAME backbone features."""
-    case = {"name": "full", "n": 1, "hw0": (480, 640), "hw1": (480, 640), "thr": 0.0, "images": "smooth"}
+_KEYS = ["b_ids", "i_ids", "j_ids", "mconf", "mkpts0_c", "mkpts1_c", "mkpts0_f", "mkpts1_f"]
+
+
+def _engine_vs_oracle(case, label, min_matches, record_as=None, feat_tol=1e-3):
+    """Engine (C ABI) vs the per-pair numpy oracle on the SAME backbone features, BASELINE.json tolerances:
+    key overlap >= 99.5 %, every non-shared match an fp64 near-tie (dual-softmax), mconf rtol 1e-3, |dxy| < 0.5 px."""
     model, data = _run_engine(case)
-    out = util.oracle_forward(case, backbone_device=DEV)
-    got = {k: data[k].cpu().numpy() for k in ["b_ids", "i_ids", "j_ids", "mconf", "mkpts0_c", "mkpts1_c", "mkpts0_f",
-                                              "mkpts1_f"]}
-    assert len(out["b_ids"]) > 300
-    stats = util.compare_matches(got, out, None, conf_rtol=1e-3, px_tol=0.5, min_overlap=0.99, label="640x480")
-    err = np.abs(data["_feat_c0"].cpu().numpy() - out["feat_c0"]).max()
-    assert err < 1e-3, f"coarse transformer output differs by {err:.3e}"
+    out, gold = util.oracle_forward_per_pair(case, backbone_device=DEV)
+    got = {k: data[k].cpu().numpy() for k in _KEYS}
+    assert len(out["b_ids"]) > min_matches, f"{label}: only {len(out['b_ids'])} oracle matches"
+    stats = util.compare_matches(got, out, gold, conf_rtol=1e-3, px_tol=0.5, min_overlap=0.995, label=label)
+    err = np.abs(data["_feat_c0"].cpu().numpy()[:, ::4] - out["feat_c0_s4"]).max()
+    assert err < feat_tol, f"{label}: coarse transformer output differs by {err:.3e}"
     stats["feat_c0_max_abs_err"] = float(err)
-    util.record("e2e_640x480_ds_vs_oracle", stats)
+    per_pair = np.bincount(got["b_ids"], minlength=case["n"])
+    assert (per_pair > 0).all(), f"{label}: a pair of the batch produced no match: {per_pair}"
+    util.record(record_as or label, stats)
+    return data, out, stats
+
+
+def test_end_to_end_640x480_vs_oracle():
+    """Config 1 of BASELINE.json (single 640x480 pair, indoor_ds) at thr 0."""
+    _engine_vs_oracle(BASELINE_CASES["full"], "640x480", 300, "e2e_640x480_ds_vs_oracle")
+
+
+def test_batch8_640x480_ds_vs_oracle():
+    """configs[1] EXACTLY as benchmarked: batch = 8 pairs 640x480, indoor_ds dual-softmax (the batch size
+    changes the chunking / partial-merge layout of the score passes and the tile schedule of every GEMM)."""
+    _engine_vs_oracle(BASELINE_CASES["b8"], "b8 640x480 ds", 8 * 300, "e2e_b8_640x480_ds_vs_oracle")
+
+
+def test_batch8_640x480_default_thr_vs_oracle():
+    """configs[1] at the cfg default thr = 0.2 (SURVEY.md §8(d) threshold caveat): with these weights no
+    confidence reaches 0.2, so both sides must return the empty list through the M = 0 path."""
+    case = BASELINE_CASES["b8thr"]
+    model, data = _run_engine(case)
+    out, _ = util.oracle_forward_per_pair(case, backbone_device=DEV, adjudicate=False)
+    assert len(out["b_ids"]) == data["b_ids"].shape[0]
+    if len(out["b_ids"]):
+        got = {k: data[k].cpu().numpy() for k in _KEYS}
+        util.compare_matches(got, out, None, conf_rtol=1e-3, px_tol=0.5, min_overlap=0.995, label="b8 thr0.2")
+    else:
+        assert data["mkpts0_f"].shape == (0, 2) and data["expec_f"].shape == (0, 3)
+
+
+def test_batch8_640x480_sinkhorn_vs_oracle():
+    """configs[4] EXACTLY as named: batch = 8 pairs 640x480, indoor_ot (Sinkhorn, 3 iterations)."""
+    _engine_vs_oracle(BASELINE_CASES["b8ot"], "b8 640x480 ot", 8 * 300, "e2e_b8_640x480_sinkhorn_vs_oracle")
+
+
+def test_outdoor_832_batch4_masked_vs_oracle():
+    """configs[2] per-GPU shard: 4 pairs 832x832 (L = S = 10816) with MegaDepth-style padding masks (a different
+    valid region per image) and scales."""
+    case = BASELINE_CASES["out4"]
+    data, out, _ = _engine_vs_oracle(case, "4x832 masked", 4 * 400, "e2e_4x832x832_masked_vs_oracle")
+    b, i, j = (data[k].cpu().numpy() for k in ("b_ids", "i_ids", "j_ids"))
+    for p in range(4):   # nothing may come from the padded area or its border  [coarse_matching.py:28-43]
+        (vh0, vw0), (vh1, vw1) = case["valid0"][p], case["valid1"][p]
+        sel = b == p
+        assert (i[sel] // 104 < vh0 // 8 - 2).all() and (i[sel] % 104 < vw0 // 8 - 2).all()
+        assert (j[sel] // 104 < vh1 // 8 - 2).all() and (j[sel] % 104 < vw1 // 8 - 2).all()
 
 
 def test_no_cpu_fallback():
@@ -230,81 +281,39 @@ def test_no_cpu_fallback():
 # ------------------------------------------------------------------------------------------------ BASELINE.json configs
 def test_outdoor_832_masked_vs_oracle():
     """configs[2] shape: 832x832 (L = S = 10816), MegaDepth-style padding masks + scales, one pair."""
-    case = {"name": "outdoor", "n": 1, "hw0": (832, 832), "hw1": (832, 832), "thr": 0.0, "images": "smooth",
-            "valid0": [(832, 624)], "valid1": [(640, 832)], "scales": True}
-    model, data = _run_engine(case)
-    out = util.oracle_forward(case, backbone_device=DEV)
-    got = {k: data[k].cpu().numpy() for k in ["b_ids", "i_ids", "j_ids", "mconf", "mkpts0_c", "mkpts1_c", "mkpts0_f",
-                                              "mkpts1_f"]}
-    assert len(out["b_ids"]) > 500
-    stats = util.compare_matches(got, out, None, conf_rtol=1e-3, px_tol=0.5, min_overlap=0.99, label="832 masked")
-    # nothing may come from the padded area or its border
-    i, j = got["i_ids"], got["j_ids"]
+    data, out, _ = _engine_vs_oracle(BASELINE_CASES["outdoor"], "832 masked", 500, "e2e_832x832_masked_vs_oracle")
+    i, j = data["i_ids"].cpu().numpy(), data["j_ids"].cpu().numpy()
     assert (i % 104 < 624 // 8 - 2).all() and (j // 104 < 640 // 8 - 2).all()
-    util.record("e2e_832x832_masked_vs_oracle", stats)
 
 
 def test_sinkhorn_640x480_vs_oracle():
     """configs[4] shape: indoor_ot at 640x480 (one pair)."""
-    case = {"name": "ot_full", "n": 1, "hw0": (480, 640), "hw1": (480, 640), "thr": 0.0, "images": "smooth",
-            "match_type": "sinkhorn"}
-    model, data = _run_engine(case)
-    out = util.oracle_forward(case, backbone_device=DEV)
-    got = {k: data[k].cpu().numpy() for k in ["b_ids", "i_ids", "j_ids", "mconf", "mkpts0_c", "mkpts1_c", "mkpts0_f",
-                                              "mkpts1_f"]}
-    assert len(out["b_ids"]) > 300
-    stats = util.compare_matches(got, out, None, conf_rtol=1e-3, px_tol=0.5, min_overlap=0.99, label="ot 640x480")
-    util.record("e2e_640x480_sinkhorn_vs_oracle", stats)
+    _engine_vs_oracle(BASELINE_CASES["ot_full"], "ot 640x480", 300, "e2e_640x480_sinkhorn_vs_oracle")
 
 
-@pytest.mark.parametrize("hw", [(240, 320), (960, 1280)])
-def test_resolution_sweep_properties(hw):
-    """configs[3]: token-count scaling.  320x240 is checked against the oracle; at 1280x960 (L = 19200, where the
-    oracle's L x S matrices no longer fit comfortably) size-independent properties are checked instead:
-    duplicate pairs in a batch give identical lists, and every reported match is a mutual nearest neighbour
-    with the reported confidence when its row / column are recomputed in fp64."""
+@pytest.mark.parametrize("hw", [(240, 320), (720, 960), (960, 1280)])
+def test_resolution_sweep_vs_oracle(hw):
+    """configs[3]: token-count scaling, L = 1200 / 10800 / 19200 (4800 is test_end_to_end_640x480_vs_oracle).  The
+    FULL match list is compared with the oracle at every size (the oracle's L x S temporaries are ~1.5 GB fp32 at
+    1280x960; the fp64 adjudication statistics are evaluated row-blocked)."""
     h, w = hw
-    case = {"name": "sweep", "n": 1, "hw0": hw, "hw1": hw, "thr": 0.0, "images": "smooth"}
-    if h * w <= 320 * 240:
-        model, data = _run_engine(case)
-        out = util.oracle_forward(case, backbone_device=DEV)
-        got = {k: data[k].cpu().numpy() for k in ["b_ids", "i_ids", "j_ids", "mconf", "mkpts0_c", "mkpts1_c",
-                                                  "mkpts0_f", "mkpts1_f"]}
-        util.compare_matches(got, out, None, conf_rtol=1e-3, px_tol=0.5, min_overlap=0.99, label=str(hw))
-        return
+    case = BASELINE_CASES[f"sweep{h}"]
+    _engine_vs_oracle(case, f"sweep {h}x{w}", (h // 8) * (w // 8) // 25, f"e2e_sweep_{h}x{w}_vs_oracle")
+
+
+def test_large_batch_duplicate_pairs_agree():
+    """Size-independent property at the largest sweep size (1280x960, L = 19200): the two copies of one pair
+    inside a batch give bit-identical lists (no cross-pair leakage, schedule-independent reductions)."""
+    case = {"name": "sweep", "n": 1, "hw0": (960, 1280), "hw1": (960, 1280), "thr": 0.0, "images": "smooth"}
     model, cfg, _ = util.build_model(case, DEV)
     inp = build_inputs(case)
     i0, i1 = _t(inp["image0"]), _t(inp["image1"])
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
-    one = {"image0": i0, "image1": i1}
-    model(one)
     two = {"image0": torch.cat([i0, i0]), "image1": torch.cat([i1, i1])}
     model(two)
-    m = one["mconf"].shape[0]
-    assert m > 1000
     nb = (two["m_bids"] == 0).sum().item()
-    assert two["mconf"].shape[0] == 2 * nb
-    for k in ("i_ids", "j_ids"):
-        assert torch.equal(two[k][:nb], two[k][nb:])            # the two copies inside one batch agree exactly
-    assert torch.equal(two["mconf"][:nb], two["mconf"][nb:])
-    # fp64 re-evaluation of sampled matches from the engine's own coarse features
-    f0, f1 = one["_feat_c0"][0].double() / 16.0, one["_feat_c1"][0].double() / 16.0   # / sqrt(256)
-    idx = torch.linspace(0, m - 1, 64, device=DEV).long()
-    ii, jj = one["i_ids"][idx], one["j_ids"][idx]
-    sim_rows = (f0[ii] @ f1.T) / 0.1                              # [64, S]
-    sim_cols = (f0 @ f1[jj].T) / 0.1                              # [L, 64]
-    row_lse = torch.logsumexp(sim_rows, 1)                        # rowLSE_i
-    col_lse = torch.logsumexp(sim_cols, 0)                        # colLSE_j
-    s_ij = sim_rows[torch.arange(64), jj]
-    conf = torch.exp(2 * s_ij - row_lse - col_lse)
-    rel = ((one["mconf"][idx].double() - conf).abs() / conf).max().item()
-    assert rel < 1e-3, f"mconf differs from the fp64 re-evaluation by {rel:.2e}"
-    # mutual nearest neighbour: j maximises 2 s_ij - colLSE_j over the row needs all colLSE; check the weaker,
-    # size-independent necessary condition on the column side: i maximises s_ij - rowLSE_i ... via rows' own LSE
-    full_row_lse = torch.cat([torch.logsumexp((f0[a:a + 2048] @ f1.T) / 0.1, 1) for a in range(0, f0.shape[0], 2048)])
-    col_key = 2 * sim_cols - full_row_lse[:, None]
-    assert torch.equal(col_key.argmax(0), ii), "a reported match is not the column's nearest neighbour"
+    assert nb > 1000 and two["mconf"].shape[0] == 2 * nb
+    for k in ("i_ids", "j_ids", "mconf", "mkpts1_f"):
+        assert torch.equal(two[k][:nb], two[k][nb:]), k
 
 
 # ------------------------------------------------------------------------------------------------ backbone on tensor cores
@@ -365,3 +374,42 @@ def test_coarse_matching_large_logit_spread():
     assert len(out["b_ids"]) > 50
     stats = util.compare_matches(got, out, None, conf_rtol=1e-3, px_tol=1e-3, min_overlap=1.0, label="spread")
     util.record("cm_large_logit_spread", stats)
+
+
+# ------------------------------------------------------------------------------------------------ host-object behaviour
+def test_packed_caches_survive_copy_pickle_and_data_mutation():
+    """after a forward the model must still deep-copy / pickle (the ctypes caches are not state), and
+    `invalidate_packed()` must make `.data` writes visible to the kernels."""
+    import copy
+    import io
+    case = dict(CASES[0])
+    model, data = _run_engine(case)
+    ref = {k: data[k].clone() for k in ("mconf", "mkpts1_f")}
+    clone = copy.deepcopy(model)
+    buf = io.BytesIO()
+    torch.save(model, buf)
+    buf.seek(0)
+    loaded = torch.load(buf, weights_only=False)
+    for m in (clone, loaded):
+        d = {k: _t(v) for k, v in build_inputs(case).items()}
+        m(d)
+        assert torch.equal(d["mconf"], ref["mconf"]) and torch.equal(d["mkpts1_f"], ref["mkpts1_f"])
+    # .data mutation is invisible to _version / data_ptr: stale until invalidate_packed()
+    w = model.loftr_coarse.layers[0].merge.weight
+    w.data.mul_(1.5)
+    d1 = {k: _t(v) for k, v in build_inputs(case).items()}
+    model(d1)
+    model.invalidate_packed()
+    d2 = {k: _t(v) for k, v in build_inputs(case).items()}
+    model(d2)
+    assert d2["mconf"].shape != ref["mconf"].shape or not torch.equal(d2["mconf"], ref["mconf"])
+    # load_state_dict invalidates by itself
+    model.load_state_dict(clone.state_dict())
+    d3 = {k: _t(v) for k, v in build_inputs(case).items()}
+    model(d3)
+    assert torch.equal(d3["mconf"], ref["mconf"])
+    assert "_feat_c0" in d3
+    clone.expose_coarse_features = False
+    d4 = {k: _t(v) for k, v in build_inputs(case).items()}
+    clone(d4)
+    assert "_feat_c0" not in d4 and "_feat_c1" not in d4

@@ -29,13 +29,14 @@ def test_struct_layouts_match_header_field_order():
     header = open(os.path.join(ROOT, "include", "loftr_b200.h")).read()
     header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
     for cls in (_lib.LbEncoderLayerWeights, _lib.LbTransformerState, _lib.LbCoarseMatchArgs,
-                _lib.LbFinePreprocessArgs, _lib.LbFineMatchArgs):
+                _lib.LbFinePreprocessArgs, _lib.LbFineMatchArgs, _lib.LbConvWeights, _lib.LbBackboneWeights):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cls.__name__, cls.__name__), header, re.S).group(1)
         names = []
         for decl in body.split(";"):
             decl = decl.strip()
             if not decl:
                 continue
+            decl = re.sub(r"\[[^\]]*\]", "", decl)   # array declarators: l1[4] -> l1
             first, *rest = decl.split(",")
             names.append(re.findall(r"[A-Za-z_0-9]+", first)[-1])
             names += [re.findall(r"[A-Za-z_0-9]+", r)[-1] for r in rest]
@@ -94,3 +95,41 @@ def test_backbone_16_4_variant_builds():
         c, f = bb(torch.rand(1, 1, 64, 96))
     assert c.shape == (1, 512, 4, 6) and f.shape == (1, 196, 16, 24)
     assert "layer4_outconv.weight" in bb.state_dict() and "layer2_outconv2.3.weight" in bb.state_dict()
+
+
+def test_model_with_packed_caches_deepcopies_and_pickles():
+    """The packed-weight caches hold ctypes structures with raw pointers; they must not enter copy / pickle state
+    (the reference module can be deep-copied, pickled and passed to mp.spawn)."""
+    import copy
+    import pickle
+    model = loftr_b200.LoFTR(loftr_b200.get_cfg("indoor_ds")).eval()
+    arr = (_lib.LbEncoderLayerWeights * 2)()
+    model.loftr_coarse._packed, model.loftr_coarse._packed_key = (arr, None, []), ("k",)
+    model.fine_preprocess._packed, model.fine_preprocess._packed_key = {"x": arr}, ("k",)
+    model._tc_backbone._packed, model._tc_backbone._key = (_lib.LbBackboneWeights(), []), ("k",)
+    c = copy.deepcopy(model)
+    p = pickle.loads(pickle.dumps(model))
+    for m in (c, p):
+        assert m.loftr_coarse._packed is None and m.fine_preprocess._packed is None and m._tc_backbone._packed is None
+        assert m._tc_backbone.m is m.backbone
+        assert set(m.state_dict()) == set(model.state_dict())
+    assert model.loftr_coarse._packed is not None          # the original keeps its cache
+    model.invalidate_packed()
+    assert model.loftr_coarse._packed is None and model._tc_backbone._packed is None
+    model.loftr_coarse._packed = (arr, None, [])
+    model.load_state_dict(c.state_dict())
+    assert model.loftr_coarse._packed is None
+    model.loftr_coarse._packed = (arr, None, [])
+    model.float()
+    assert model.loftr_coarse._packed is None
+
+
+def test_unsupported_shapes_fail_at_construction():
+    cfg = loftr_b200.get_cfg("indoor_ds")
+    cfg["coarse"]["nhead"] = 4
+    with pytest.raises(ValueError, match="coarse transformer"):
+        loftr_b200.LoFTR(cfg)
+    cfg = loftr_b200.get_cfg("indoor_ds")
+    cfg["fine_window_size"] = 7
+    with pytest.raises(ValueError, match="fine windows"):
+        loftr_b200.LoFTR(cfg)
