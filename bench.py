@@ -228,6 +228,8 @@ def run_b200(args):
         dist.all_gather_into_tensor(out, t)
         return out.tolist()
 
+    gatherer = [None]   # library-side NCCL communicator (created after the torch process group)
+
     class Workload:
         """One (cfg, batch, image size) configuration: model, device + pinned-host inputs, step functions."""
 
@@ -251,7 +253,7 @@ def run_b200(args):
             return data
 
         def gather(self, data):
-            return parallel.all_gather_matches(data, self.lo_pair, self.cap)
+            return parallel.all_gather_matches(data, self.lo_pair, self.cap, gatherer=gatherer[0])
 
         def step(self):
             data = self.local_step()
@@ -320,7 +322,7 @@ def run_b200(args):
     for wl in [main] + [w for _, w in extras]:
         for _ in range(Wm if wl is main else 2):
             last_wl = wl.local_step()
-            parallel.unpack_matches(parallel.pack_matches(last_wl, wl.lo_pair, wl.cap).unsqueeze(0))
+            parallel.unpack_matches(parallel.pack_matches(last_wl, wl.lo_pair, 16384).unsqueeze(0))
         if wl is main:
             last = last_wl
     m_per_step = int(last["mconf"].shape[0])
@@ -335,7 +337,8 @@ def run_b200(args):
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
-        note("process group up")
+        gatherer[0] = parallel.MatchGatherer(dev)
+        note("process group + library communicator up")
         for wl in [main] + [w for _, w in extras]:   # collective warm-up (NCCL channels, all-gather kernel)
             for _ in range(2):
                 wl.step()
@@ -489,6 +492,7 @@ def run_b200(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        gatherer[0].close()
         dist.destroy_process_group()
 
 

@@ -235,6 +235,28 @@ typedef struct LbFineMatchArgs {
 
 int lb_fine_match(const LbFineMatchArgs* args /*host*/, void* stream);
 
+/* ---- multi-GPU: all-gather of the match lists.  Pairs are sharded over ranks (one process per GPU); every rank ends
+ * with the global list.  Replaces the reference's gather() (src/utils/comm.py:113-176, called from
+ * src/lightning/lightning_loftr.py:235,241: a size exchange plus a padded pickled-object all_gather on a gloo side
+ * group) with ONE static-shape ncclAllGather on the compute stream between a pack and an unpack kernel.
+ * Wire buffer per rank: float32 [1 + capacity][6]; row 0 = (count, 0...), row 1+k = (x0, y0, x1, y1, mconf, global
+ * pair id).  NCCL is bound at run time (dlopen of libnccl.so.2; `nccl_lib_path` / LOFTR_B200_NCCL_LIB override it). */
+#define LB_NCCL_UNIQUE_ID_BYTES 128
+/* rank 0: create the rendezvous id (host buffer of LB_NCCL_UNIQUE_ID_BYTES), ship it to the other ranks out of band */
+int lb_comm_unique_id(char* id_out /*host*/, const char* nccl_lib_path /*host, optional*/);
+int lb_comm_init(const char* id_bytes /*host*/, int rank, int world, int device, const char* nccl_lib_path /*host, optional*/,
+                 void** comm_out /*host*/);
+int lb_comm_destroy(void* comm);
+/* this rank's matcher outputs (`count` rows; pair ids are offset by `pair_offset`) -> wire buffer */
+int lb_pack_matches(const float* mkpts0_f, const float* mkpts1_f, const float* mconf, const long long* m_bids,
+                    long count, int pair_offset, float* wire, long capacity, void* stream);
+/* wire_send [1 + capacity][6] of every rank -> wire_recv [world][1 + capacity][6] on every rank */
+int lb_allgather_matches(void* comm, const float* wire_send, float* wire_recv, long capacity, void* stream);
+/* wire_recv -> concatenated lists in rank order (= ascending (pair, i) for contiguous pair blocks); counts_out
+ * [world + 1] device ints: the per-rank counts as sent (a count > capacity signals overflow) and the stored total */
+int lb_unpack_matches(const float* wire_recv, int world, long capacity, float* mkpts0_f, float* mkpts1_f, float* mconf,
+                      long long* m_bids, long out_capacity, int* counts_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

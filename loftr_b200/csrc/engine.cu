@@ -16,6 +16,7 @@
 #include "epilogues.cuh"
 #include "gemm_split.cuh"
 #include "simt_kernels.cuh"
+#include "comm.cuh"
 
 namespace lb {
 
@@ -1321,6 +1322,87 @@ int lb_fine_match(const LbFineMatchArgs* a, void* stream) {
   p.mkpts1_c = a->mkpts1_c; p.expec_f = a->expec_f; p.mkpts1_f = a->mkpts1_f;
   const int warps_per_block = 8;
   fine_match_kernel<<<cdiv(a->M, warps_per_block), warps_per_block * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  LB_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU
+int lb_comm_unique_id(char* id_out, const char* nccl_lib_path) {
+  NcclApi* api = nccl_api(nccl_lib_path);
+  if (!api) return fail("NCCL library not found (dlopen of libnccl.so.2 failed; set LOFTR_B200_NCCL_LIB)");
+  NcclApi::UniqueId id;
+  const int rc = api->GetUniqueId(&id);
+  if (rc != 0) return fail("ncclGetUniqueId failed: %s", api->GetErrorString ? api->GetErrorString(rc) : "?");
+  memcpy(id_out, id.internal, LB_NCCL_UNIQUE_ID_BYTES);
+  return 0;
+}
+
+int lb_comm_init(const char* id_bytes, int rank, int world, int device, const char* nccl_lib_path, void** comm_out) {
+  if (!id_bytes || !comm_out || world <= 0 || rank < 0 || rank >= world) return fail("lb_comm_init: bad arguments");
+  NcclApi* api = nccl_api(nccl_lib_path);
+  if (!api) return fail("NCCL library not found (dlopen of libnccl.so.2 failed; set LOFTR_B200_NCCL_LIB)");
+  int prev = -1;
+  LB_CUDA(cudaGetDevice(&prev));
+  LB_CUDA(cudaSetDevice(device));
+  int sms;
+  int rc0 = device_check(&sms);
+  if (rc0) {
+    cudaSetDevice(prev);
+    return rc0;
+  }
+  NcclApi::UniqueId id;
+  memcpy(id.internal, id_bytes, LB_NCCL_UNIQUE_ID_BYTES);
+  void* nccl = nullptr;
+  const int rc = api->CommInitRank(&nccl, world, id, rank);
+  cudaSetDevice(prev);
+  if (rc != 0) return fail("ncclCommInitRank failed: %s", api->GetErrorString ? api->GetErrorString(rc) : "?");
+  *comm_out = new LbComm{nccl, rank, world, device};
+  return 0;
+}
+
+int lb_comm_destroy(void* comm) {
+  if (!comm) return 0;
+  LbComm* c = static_cast<LbComm*>(comm);
+  NcclApi* api = nccl_api(nullptr);
+  if (api && c->nccl) api->CommDestroy(c->nccl);
+  delete c;
+  return 0;
+}
+
+int lb_pack_matches(const float* mkpts0_f, const float* mkpts1_f, const float* mconf, const long long* m_bids,
+                    long count, int pair_offset, float* wire, long capacity, void* stream) {
+  DeviceGuard dev_guard;
+  LB_TRY(dev_guard.bind(wire));
+  if (count > capacity) return fail("lb_pack_matches: %ld matches exceed the wire capacity %ld", count, capacity);
+  if (count > 0 && (!mkpts0_f || !mkpts1_f || !mconf || !m_bids)) return fail("lb_pack_matches: null input");
+  const long n = count > 0 ? count : 1;
+  pack_matches_kernel<<<cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(mkpts0_f, mkpts1_f, mconf, m_bids, count,
+                                                                                    pair_offset, wire, capacity);
+  LB_LAUNCHED();
+  return 0;
+}
+
+int lb_allgather_matches(void* comm, const float* wire_send, float* wire_recv, long capacity, void* stream) {
+  if (!comm) return fail("lb_allgather_matches: null communicator");
+  LbComm* c = static_cast<LbComm*>(comm);
+  DeviceGuard dev_guard;
+  LB_TRY(dev_guard.bind(wire_recv));
+  NcclApi* api = nccl_api(nullptr);
+  if (!api) return fail("NCCL library not loaded");
+  const size_t count = static_cast<size_t>(1 + capacity) * kWireCols;
+  const int rc = api->AllGather(wire_send, wire_recv, count, kNcclFloat32, c->nccl, static_cast<cudaStream_t>(stream));
+  if (rc != 0) return fail("ncclAllGather failed: %s", api->GetErrorString ? api->GetErrorString(rc) : "?");
+  return 0;
+}
+
+int lb_unpack_matches(const float* wire_recv, int world, long capacity, float* mkpts0_f, float* mkpts1_f, float* mconf,
+                      long long* m_bids, long out_capacity, int* counts_out, void* stream) {
+  DeviceGuard dev_guard;
+  LB_TRY(dev_guard.bind(wire_recv));
+  if (world <= 0 || capacity < 0) return fail("lb_unpack_matches: bad arguments");
+  const long n = capacity > 0 ? capacity : 1;
+  unpack_matches_kernel<<<dim3(cdiv(n, 256), world), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      wire_recv, world, capacity, mkpts0_f, mkpts1_f, mconf, m_bids, out_capacity, counts_out);
   LB_LAUNCHED();
   return 0;
 }

@@ -81,6 +81,130 @@ __device__ __forceinline__ void load_planes32(const __half* hp, const __half* lp
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Coalesced epilogue I/O.  An epilogue thread owns one accumulator ROW, so a warp-wide 16-byte store of "my row's
+// next 16 bytes" touches 32 different cache lines (32 sectors per request: the L1 tag stage, not DRAM, becomes the
+// limiter -- l1tex at 70-75 % in the round-1 ncu captures).  These helpers transpose a [32 rows x 64 B] block through
+// a 2 KB per-warp shared-memory scratch (XOR-swizzled, bank-conflict free both ways) so that every global access
+// instruction covers 8 rows x 64 contiguous bytes.  Rows are addressed by a per-lane pointer (lane = row; nullptr =
+// row not stored / read as zero), so the same code serves row-major matrices and NHWC pixel rows.
+#ifndef LB_COALESCE
+#define LB_COALESCE 1
+#endif
+constexpr int kEpiScratchBytes = LB_COALESCE ? 8 * 2048 : 0;   // 8 epilogue warps x 2 KB
+__device__ __forceinline__ uint32_t* epi_scratch(uint8_t* base) {
+  return reinterpret_cast<uint32_t*>(base + ((epi_tid() >> 5) << 11));
+}
+template <class T>
+__device__ __forceinline__ T* shfl_ptr(T* p, int src_lane) {
+  const unsigned long long v = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(p), src_lane);
+  return reinterpret_cast<T*>(v);
+}
+// w[16]: 64 bytes of this lane's row -> *(row_ptr + 0..63) for every lane with row_ptr != nullptr
+__device__ __forceinline__ void warp_store_rows64(uint32_t* scr, uint8_t* row_ptr, const uint32_t (&w)[16]) {
+#if LB_COALESCE
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<uint4*>(scr + lane * 16 + ((q ^ ((lane >> 1) & 3)) << 2)) =
+        make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+  __syncwarp();
+  const int g = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane >> 2) + 8 * i;
+    uint8_t* dst = shfl_ptr(row_ptr, r);
+    const uint4 v = *reinterpret_cast<const uint4*>(scr + r * 16 + ((g ^ ((r >> 1) & 3)) << 2));
+    if (dst) *reinterpret_cast<uint4*>(dst + g * 16) = v;
+  }
+#else
+  (void)scr;
+  if (row_ptr) {
+    uint4* d = reinterpret_cast<uint4*>(row_ptr);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) d[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+  }
+#endif
+}
+// inverse: 64 bytes at row_ptr (zeros for nullptr) -> w[16] of the owning lane
+__device__ __forceinline__ void warp_load_rows64(uint32_t* scr, const uint8_t* row_ptr, uint32_t (&w)[16]) {
+#if LB_COALESCE
+  const int lane = threadIdx.x & 31;
+  const int g = lane & 3;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane >> 2) + 8 * i;
+    const uint8_t* src = shfl_ptr(row_ptr, r);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (src) v = *reinterpret_cast<const uint4*>(src + g * 16);
+    *reinterpret_cast<uint4*>(scr + r * 16 + ((g ^ ((r >> 1) & 3)) << 2)) = v;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 v = *reinterpret_cast<const uint4*>(scr + lane * 16 + ((q ^ ((lane >> 1) & 3)) << 2));
+    w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+  }
+#else
+  (void)scr;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row_ptr) v = reinterpret_cast<const uint4*>(row_ptr)[q];
+    w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+  }
+#endif
+}
+// 32 values of my row as fp16 hi/lo planes: hi_ptr / lo_ptr address (row, first column) or nullptr
+__device__ __forceinline__ void warp_store_planes32(uint32_t* scr, __half* hi_ptr, __half* lo_ptr, const float (&x)[32]) {
+  uint32_t h[16], l[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    __half h0, l0, h1, l1;
+    split_f16(x[2 * j], h0, l0);
+    split_f16(x[2 * j + 1], h1, l1);
+    h[j] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
+    l[j] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
+  }
+  warp_store_rows64(scr, reinterpret_cast<uint8_t*>(hi_ptr), h);
+  warp_store_rows64(scr, reinterpret_cast<uint8_t*>(lo_ptr), l);
+}
+__device__ __forceinline__ void warp_store_f32x32(uint32_t* scr, float* ptr, const float (&x)[32]) {
+  uint32_t a[16], b[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    a[j] = __float_as_uint(x[j]);
+    b[j] = __float_as_uint(x[16 + j]);
+  }
+  warp_store_rows64(scr, reinterpret_cast<uint8_t*>(ptr), a);
+  warp_store_rows64(scr, ptr ? reinterpret_cast<uint8_t*>(ptr) + 64 : nullptr, b);
+}
+__device__ __forceinline__ void warp_load_planes32(uint32_t* scr, const __half* hi_ptr, const __half* lo_ptr, float (&x)[32]) {
+  uint32_t h[16], l[16];
+  warp_load_rows64(scr, reinterpret_cast<const uint8_t*>(hi_ptr), h);
+  warp_load_rows64(scr, reinterpret_cast<const uint8_t*>(lo_ptr), l);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+    const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&l[j]));
+    x[2 * j] = fh.x + fl.x;
+    x[2 * j + 1] = fh.y + fl.y;
+  }
+}
+__device__ __forceinline__ void warp_load_f32x32(uint32_t* scr, const float* ptr, float (&x)[32]) {
+  uint32_t a[16], b[16];
+  warp_load_rows64(scr, reinterpret_cast<const uint8_t*>(ptr), a);
+  warp_load_rows64(scr, ptr ? reinterpret_cast<const uint8_t*>(ptr) + 64 : nullptr, b);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    x[j] = __uint_as_float(a[j]);
+    x[16 + j] = __uint_as_float(b[j]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // out[row, col] = act(acc) * rowmask[row];  act = elu(x)+1 for col < elu_cols, identity otherwise.
 // Covers q/k/v projection + feature map + padding mask of LinearAttention
@@ -94,10 +218,11 @@ struct EpiActStore {
     const uint8_t* rowmask;  // optional [batches*M] (1 = valid)
     float acc_scale;         // 2^-e: undoes the power-of-two pre-scaling of the weight planes (exact)
   };
-  static constexpr int kSmemBytes = 0;
+  static constexpr int kSmemBytes = kEpiScratchBytes;
   const Params& p;
   const GemmShape& s;
-  __device__ EpiActStore(const Params& p_, uint8_t*, const GemmShape& s_) : p(p_), s(s_) {}
+  uint32_t* scr;
+  __device__ EpiActStore(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_), scr(epi_scratch(smem)) {}
   __device__ void item_begin(int, int, int) {}
   __device__ void item_end(int, int, int) {}
   __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
@@ -121,7 +246,7 @@ struct EpiActStore {
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] *= mk;
-      if (row_ok) store_f32x32(p.out + grow * p.ld + col, x);
+      warp_store_f32x32(scr, row_ok ? p.out + grow * p.ld + col : nullptr, x);
     }
   }
 };
@@ -360,13 +485,15 @@ struct EpiLayerNorm {
     int pl_col0;
     float acc_scale;        // 2^-e of the weight planes
   };
-  static constexpr int kSmemBytes = 2 * BLOCK_N * 4 + 2 * 128 * 4;
+  static constexpr int kSmemBytes = kEpiScratchBytes + 2 * BLOCK_N * 4 + 2 * 128 * 4;
   const Params& p;
   const GemmShape& s;
   float* sg;
   float* sb;
   float* s_red;  // [2 halves][128 rows]
-  __device__ EpiLayerNorm(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_) {
+  uint32_t* scr;
+  __device__ EpiLayerNorm(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_), scr(epi_scratch(smem)) {
+    smem += kEpiScratchBytes;
     sg = reinterpret_cast<float*>(smem);
     sb = sg + BLOCK_N;
     s_red = sb + BLOCK_N;
@@ -420,29 +547,24 @@ struct EpiLayerNorm {
       load_acc32(tmem_acc, c * 32, x);
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = (x[j] * p.acc_scale - mean) * rstd * sg[c * 32 + j] + sb[c * 32 + j];
-      if (row_ok) {
-        if (p.residual) {
-          const float4* rp = reinterpret_cast<const float4*>(p.residual + grow * p.ld_res + c * 32);
+      // warp-cooperative (coalesced) residual loads and stores: every lane takes part, invalid rows pass nullptr
+      if (p.residual) {
+        float r[32];
+        warp_load_f32x32(scr, row_ok ? p.residual + grow * p.ld_res + c * 32 : nullptr, r);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 t = rp[j];
-            x[4 * j] += t.x;
-            x[4 * j + 1] += t.y;
-            x[4 * j + 2] += t.z;
-            x[4 * j + 3] += t.w;
-          }
-        }
-        if (p.res_hi) {
-          float r[32];
-          load_planes32(p.res_hi + grow * p.ld_res_pl + c * 32, p.res_lo + grow * p.ld_res_pl + c * 32, r);
+        for (int j = 0; j < 32; ++j) x[j] += r[j];
+      }
+      if (p.res_hi) {
+        float r[32];
+        warp_load_planes32(scr, row_ok ? p.res_hi + grow * p.ld_res_pl + c * 32 : nullptr,
+                           row_ok ? p.res_lo + grow * p.ld_res_pl + c * 32 : nullptr, r);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] += r[j];
-        }
-        if (p.out_f32) store_f32x32(p.out_f32 + grow * p.ld_f32 + c * 32, x);
-        if (p.out_hi) {
-          const long off = grow * p.ld_pl + p.pl_col0 + c * 32;
-          store_planes32(p.out_hi + off, p.out_lo + off, x);
-        }
+        for (int j = 0; j < 32; ++j) x[j] += r[j];
+      }
+      if (p.out_f32) warp_store_f32x32(scr, row_ok ? p.out_f32 + grow * p.ld_f32 + c * 32 : nullptr, x);
+      if (p.out_hi) {
+        const long off = grow * p.ld_pl + p.pl_col0 + c * 32;
+        warp_store_planes32(scr, row_ok ? p.out_hi + off : nullptr, row_ok ? p.out_lo + off : nullptr, x);
       }
     }
   }
@@ -467,10 +589,11 @@ struct EpiPlanes {
     int pl_col0;
     float acc_scale;      // 2^-e of the weight planes
   };
-  static constexpr int kSmemBytes = 0;
+  static constexpr int kSmemBytes = kEpiScratchBytes;
   const Params& p;
   const GemmShape& s;
-  __device__ EpiPlanes(const Params& p_, uint8_t*, const GemmShape& s_) : p(p_), s(s_) {}
+  uint32_t* scr;
+  __device__ EpiPlanes(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_), scr(epi_scratch(smem)) {}
   __device__ void item_begin(int, int, int) {}
   __device__ void item_end(int, int, int) {}
   __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
@@ -503,12 +626,10 @@ struct EpiPlanes {
           x[4 * j + 3] += t.w;
         }
       }
-      if (row_ok) {
-        if (p.out_f32) store_f32x32(p.out_f32 + grow * p.ld_f32 + col, x);
-        if (p.out_hi) {
-          const long off = grow * p.ld_pl + p.pl_col0 + col;
-          store_planes32(p.out_hi + off, p.out_lo + off, x);
-        }
+      if (p.out_f32) warp_store_f32x32(scr, row_ok ? p.out_f32 + grow * p.ld_f32 + col : nullptr, x);
+      if (p.out_hi) {
+        const long off = grow * p.ld_pl + p.pl_col0 + col;
+        warp_store_planes32(scr, row_ok ? p.out_hi + off : nullptr, row_ok ? p.out_lo + off : nullptr, x);
       }
     }
   }
@@ -545,13 +666,14 @@ struct EpiConv {
   static constexpr int kChunks = (BLOCK_N + 31) / 32;        // 32-column groups of the tile (the last may be partial)
   static constexpr int kChunksHalf0 = (kChunks + 1) / 2;     // column half 0 takes the first ones
   static constexpr int kCols = kChunks * 32;
-  static constexpr int kSmemBytes = 2 * kCols * 4;
+  static constexpr int kSmemBytes = kEpiScratchBytes + 2 * kCols * 4;
   const Params& p;
   const GemmShape& s;
   float* s_scale;
   float* s_shift;
-  __device__ EpiConv(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_) {
-    s_scale = reinterpret_cast<float*>(smem);
+  uint32_t* scr;
+  __device__ EpiConv(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_), scr(epi_scratch(smem)) {
+    s_scale = reinterpret_cast<float*>(smem + kEpiScratchBytes);
     s_shift = s_scale + kCols;
   }
   __device__ void item_begin(int, int, int) {}
@@ -602,31 +724,31 @@ struct EpiConv {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += corr[j];
       }
-      if (!ok) continue;
-      const int nvalid = min(32, s.N - col);
+      const int nvalid = min(32, s.N - col);   // warp-uniform
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], s_scale[c * 32 + j], s_shift[c * 32 + j]);
       if (nvalid == 32) {
+        // full 32-channel group: warp-cooperative (coalesced) loads / stores, pixels outside the image pass nullptr
         if (p.res_hi) {
           float r[32];
-          load_planes32(p.res_hi + pix * p.res_ld + col, p.res_lo + pix * p.res_ld + col, r);
+          warp_load_planes32(scr, ok ? p.res_hi + pix * p.res_ld + col : nullptr, ok ? p.res_lo + pix * p.res_ld + col : nullptr, r);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += r[j];
         }
         if (p.up_hi) {
           float a[32], b[32];
-          load_planes32(p.up_hi + u00 + col, p.up_lo + u00 + col, a);
-          load_planes32(p.up_hi + u01 + col, p.up_lo + u01 + col, b);
+          warp_load_planes32(scr, ok ? p.up_hi + u00 + col : nullptr, ok ? p.up_lo + u00 + col : nullptr, a);
+          warp_load_planes32(scr, ok ? p.up_hi + u01 + col : nullptr, ok ? p.up_lo + u01 + col : nullptr, b);
           const float wy0 = 1.f - wy1, wx0 = 1.f - wx1;
           float top[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) top[j] = wx0 * a[j] + wx1 * b[j];
-          load_planes32(p.up_hi + u10 + col, p.up_lo + u10 + col, a);
-          load_planes32(p.up_hi + u11 + col, p.up_lo + u11 + col, b);
+          warp_load_planes32(scr, ok ? p.up_hi + u10 + col : nullptr, ok ? p.up_lo + u10 + col : nullptr, a);
+          warp_load_planes32(scr, ok ? p.up_hi + u11 + col : nullptr, ok ? p.up_lo + u11 + col : nullptr, b);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += wy0 * top[j] + wy1 * (wx0 * a[j] + wx1 * b[j]);
         }
-      } else {
+      } else if (ok) {
         // channel tail (e.g. 196 = 6*32 + 4): scalar path
         const float wy0 = 1.f - wy1, wx0 = 1.f - wx1;
         for (int j = 0; j < nvalid; ++j) {
@@ -648,9 +770,10 @@ struct EpiConv {
         for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.01f * v[j];
       }
       if (nvalid == 32) {
-        if (p.out_f32) store_f32x32(p.out_f32 + pix * p.f32_ld + col, v);
-        if (p.out_hi) store_planes32(p.out_hi + pix * p.out_ld + col, p.out_lo + pix * p.out_ld + col, v);
-      } else {
+        if (p.out_f32) warp_store_f32x32(scr, ok ? p.out_f32 + pix * p.f32_ld + col : nullptr, v);
+        if (p.out_hi)
+          warp_store_planes32(scr, ok ? p.out_hi + pix * p.out_ld + col : nullptr, ok ? p.out_lo + pix * p.out_ld + col : nullptr, v);
+      } else if (ok) {
         for (int j = 0; j < nvalid; ++j) {
           if (p.out_f32) p.out_f32[pix * p.f32_ld + col + j] = v[j];
           if (p.out_hi) {

@@ -38,8 +38,13 @@ def _worker(rank, world, port, n_pairs, q):
     model(data)   # first forward before the communicator exists (cuDNN module loading is ~55 s slower after it)
     torch.cuda.synchronize()
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    cap = -(-n_pairs // world) * 12 * 16   # identical on every rank: the collective has static shapes
-    out = parallel.all_gather_matches(data, lo, capacity=cap)
+    # library-side communicator (C ABI: lb_comm_init / lb_allgather_matches); starts with a deliberately small
+    # capacity so that the overflow -> grow -> re-send protocol is exercised as well
+    gatherer = parallel.MatchGatherer(torch.device("cuda", rank), initial=16)
+    out = parallel.all_gather_matches(data, lo, capacity=0, gatherer=gatherer)
+    assert gatherer.capacity >= 2 * max(out["counts"])
+    out2 = parallel.all_gather_matches(data, lo, capacity=0, gatherer=gatherer)   # steady state: no re-send
+    assert all(torch.equal(out[k], out2[k]) for k in ("mkpts0_f", "mkpts1_f", "mconf", "m_bids"))
     res = {k: (v.cpu().numpy() if torch.is_tensor(v) else v) for k, v in out.items()}
     if rank == 0:  # single-GPU run of the whole batch for comparison
         full = {k: torch.from_numpy(v).to("cuda:0") for k, v in inp.items()}
@@ -47,6 +52,7 @@ def _worker(rank, world, port, n_pairs, q):
         res["full"] = {k: full[k].cpu().numpy() for k in ("mkpts0_f", "mkpts1_f", "mconf", "m_bids")}
     q.put((rank, res))
     dist.barrier()
+    gatherer.close()
     dist.destroy_process_group()
 
 

@@ -7,7 +7,7 @@
 tag="${1:-r2}"
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-NCU="ncu --clock-control none --profile-from-start off"
+NCU="ncu --clock-control none --profile-from-start off --kernel-name-base demangled"
 timeout 600 $NCU --metrics gpu__time_duration.sum --csv --log-file gpurun_out/${tag}_launches.csv \
   python tools/profile_step.py > gpurun_out/${tag}_launches.out 2>&1
 FULL="--set full --import-source on"
