@@ -593,17 +593,17 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
     if (self_pass) {
       Planes A{cat_hi + x_base * ldc, cat_lo + x_base * ldc, ldc, 0};
       Planes B{lw.wqkv_hi, lw.wqkv_lo, C, 0};
-      typename Epi::Params ep{w.qkv + x_base * 3 * C, 3 * C, 2 * C, mask ? mask + x_base : nullptr, lw.s_qkv};
+      typename Epi::Params ep{w.qkv + x_base * 3 * C, 3 * C, 2 * C, mask ? mask + x_base : nullptr, lw.s_qkv, 0};
       LB_TRY((launch_gemm<BN, Epi>(TAG_PROJ, A, B, 1, static_cast<int>(x_rows), 3 * C, C, 0, ep, stream)));
     } else {
       Planes Aq{cat_hi + x_base * ldc, cat_lo + x_base * ldc, ldc, 0};
       Planes Bq{lw.wqkv_hi, lw.wqkv_lo, C, 0};
-      typename Epi::Params eq{w.qkv + x_base * 3 * C, 3 * C, C, mask ? mask + x_base : nullptr, lw.s_qkv};
+      typename Epi::Params eq{w.qkv + x_base * 3 * C, 3 * C, C, mask ? mask + x_base : nullptr, lw.s_qkv, 0};
       LB_TRY((launch_gemm<BN, Epi>(TAG_PROJ, Aq, Bq, 1, static_cast<int>(x_rows), C, C, 0, eq, stream)));
       Planes Ak{cat_hi + s_base * ldc, cat_lo + s_base * ldc, ldc, 0};
       Planes Bk{static_cast<const __half*>(lw.wqkv_hi) + static_cast<long>(C) * C,
                 static_cast<const __half*>(lw.wqkv_lo) + static_cast<long>(C) * C, C, 0};
-      typename Epi::Params ek{w.qkv + s_base * 3 * C + C, 3 * C, C, mask ? mask + s_base : nullptr, lw.s_qkv};
+      typename Epi::Params ek{w.qkv + s_base * 3 * C + C, 3 * C, C, mask ? mask + s_base : nullptr, lw.s_qkv, 0};
       LB_TRY((launch_gemm<BN, Epi>(TAG_PROJ, Ak, Bk, 1, static_cast<int>(s_rows), 2 * C, C, 0, ek, stream)));
     }
   }
@@ -865,13 +865,15 @@ int lb_gemm_split(const void* a_hi, const void* a_lo, long lda, long a_batch_str
   Planes A{a_hi, a_lo, lda, batches > 1 ? a_batch_stride : 0};
   Planes B{b_hi, b_lo, ldb, b_batch_stride};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const char* pe = getenv("LOFTR_B200_PROBE_NULL_EPI");   // measurement probe of the main loop (tools/gemm_probe.py)
+  const int skip = pe ? atoi(pe) : 0;
   if (N % 256 == 0 || N > 128) {
     using Epi = EpiActStore<256>;
-    Epi::Params ep{out, static_cast<int>(ldo), 0, nullptr, 1.f};
+    Epi::Params ep{out, static_cast<int>(ldo), 0, nullptr, 1.f, skip};
     return launch_gemm<256, Epi>(TAG_GEMM_TEST, A, B, batches, M, N, K, 0, ep, st);
   }
   using Epi = EpiActStore<128>;
-  Epi::Params ep{out, static_cast<int>(ldo), 0, nullptr, 1.f};
+  Epi::Params ep{out, static_cast<int>(ldo), 0, nullptr, 1.f, skip};
   return launch_gemm<128, Epi>(TAG_GEMM_TEST, A, B, batches, M, N, K, 0, ep, st);
 }
 

@@ -184,8 +184,44 @@ __device__ __forceinline__ void warp_store_f32x32(uint32_t* scr, float* ptr, con
 }
 __device__ __forceinline__ void warp_load_planes32(uint32_t* scr, const __half* hi_ptr, const __half* lo_ptr, float (&x)[32]) {
   uint32_t h[16], l[16];
+#if LB_COALESCE
+  // all eight 16-byte global loads of the lane are issued before the first one is consumed (one exposed latency)
+  const int lane = threadIdx.x & 31;
+  const int g = lane & 3;
+  uint4 vh[4], vl[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane >> 2) + 8 * i;
+    const uint8_t* sh = shfl_ptr(reinterpret_cast<const uint8_t*>(hi_ptr), r);
+    const uint8_t* sl = shfl_ptr(reinterpret_cast<const uint8_t*>(lo_ptr), r);
+    vh[i] = make_uint4(0u, 0u, 0u, 0u);
+    vl[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (sh) vh[i] = *reinterpret_cast<const uint4*>(sh + g * 16);
+    if (sl) vl[i] = *reinterpret_cast<const uint4*>(sl + g * 16);
+  }
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = (lane >> 2) + 8 * i;
+      *reinterpret_cast<uint4*>(scr + r * 16 + ((g ^ ((r >> 1) & 3)) << 2)) = pass == 0 ? vh[i] : vl[i];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 v = *reinterpret_cast<const uint4*>(scr + lane * 16 + ((q ^ ((lane >> 1) & 3)) << 2));
+      if (pass == 0) {
+        h[4 * q] = v.x; h[4 * q + 1] = v.y; h[4 * q + 2] = v.z; h[4 * q + 3] = v.w;
+      } else {
+        l[4 * q] = v.x; l[4 * q + 1] = v.y; l[4 * q + 2] = v.z; l[4 * q + 3] = v.w;
+      }
+    }
+  }
+#else
   warp_load_rows64(scr, reinterpret_cast<const uint8_t*>(hi_ptr), h);
   warp_load_rows64(scr, reinterpret_cast<const uint8_t*>(lo_ptr), l);
+#endif
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
@@ -217,6 +253,7 @@ struct EpiActStore {
     int elu_cols;            // columns [0, elu_cols) get elu+1
     const uint8_t* rowmask;  // optional [batches*M] (1 = valid)
     float acc_scale;         // 2^-e: undoes the power-of-two pre-scaling of the weight planes (exact)
+    int skip;                // probe mode (LOFTR_B200_PROBE_NULL_EPI=1, lb_gemm_split only): 1 = drain nothing, 2 = TMEM loads only
   };
   static constexpr int kSmemBytes = kEpiScratchBytes;
   const Params& p;
@@ -225,7 +262,9 @@ struct EpiActStore {
   __device__ EpiActStore(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_), scr(epi_scratch(smem)) {}
   __device__ void item_begin(int, int, int) {}
   __device__ void item_end(int, int, int) {}
+  __device__ void prefetch(int, int, int) {}
   __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
+    if (p.skip == 1) return;
     const int r = m0 + epi_row();
     const bool row_ok = r < s.M;
     const long grow = static_cast<long>(batch) * s.M + r;
@@ -238,6 +277,13 @@ struct EpiActStore {
       if (col >= s.N) break;  // warp-uniform
       float x[32];
       load_acc32(tmem_acc, c * 32, x);
+      if (p.skip == 2) {   // keep the loads alive without storing
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc += x[j];
+        if (acc == 1.2345e-30f) p.out[0] = acc;
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] *= p.acc_scale;
       if (col < p.elu_cols) {
@@ -289,6 +335,7 @@ struct EpiKv {
   }
   __device__ void item_begin(int, int, int) {}
   __device__ void item_end(int, int, int) {}
+  __device__ void prefetch(int, int, int) {}
   __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
     const int t = epi_tid();
     const int row = epi_row();
@@ -408,6 +455,7 @@ struct EpiAttn {
     }
   }
   __device__ void item_end(int, int, int) {}
+  __device__ void prefetch(int, int, int) {}
   __device__ void tile(uint32_t tmem_acc, int batch, int m0, int) {
     const int r = m0 + epi_row();
     const bool row_ok = r < s.M;
@@ -485,7 +533,7 @@ struct EpiLayerNorm {
     int pl_col0;
     float acc_scale;        // 2^-e of the weight planes
   };
-  static constexpr int kSmemBytes = kEpiScratchBytes + 2 * BLOCK_N * 4 + 2 * 128 * 4;
+  static constexpr int kSmemBytes = kEpiScratchBytes + 2 * BLOCK_N * 4 + 2 * 128 * 8 + 128 * 4;
   const Params& p;
   const GemmShape& s;
   float* sg;
@@ -505,14 +553,31 @@ struct EpiLayerNorm {
   }
   __device__ void item_begin(int, int, int) {}
   __device__ void item_end(int, int, int) {}
-  // the two threads that share a row (column halves) exchange their partial sums through smem
-  __device__ float row_total(float part) {
+  // pull this thread's residual segments towards L2 while the tensor core is still producing the tile
+  __device__ void prefetch(int batch, int m0, int) {
+    const int r = m0 + epi_row();
+    if (r >= s.M) return;
+    const long grow = static_cast<long>(batch) * s.M + r;
+    const int c0 = epi_half() * (BLOCK_N / 2);
+    if (p.res_hi) {
+      for (int c = 0; c < BLOCK_N / 2; c += 64) {   // 64 fp16 = one 128-byte line
+        prefetch_l2(p.res_hi + grow * p.ld_res_pl + c0 + c);
+        prefetch_l2(p.res_lo + grow * p.ld_res_pl + c0 + c);
+      }
+    }
+    if (p.residual) {
+      for (int c = 0; c < BLOCK_N / 2; c += 32) prefetch_l2(p.residual + grow * p.ld_res + c0 + c);
+    }
+  }
+  // the two threads that share a row (column halves) exchange their partial (sum, sum of squares) through smem
+  __device__ float2 row_total2(float a, float b) {
     const int row = epi_row(), half = epi_half();
-    s_red[half * 128 + row] = part;
+    float2* red = reinterpret_cast<float2*>(s_red);
+    red[half * 128 + row] = make_float2(a, b);
     epi_bar_sync();
-    const float tot = s_red[row] + s_red[128 + row];
+    const float2 u = red[row], v = red[128 + row];
     epi_bar_sync();
-    return tot;
+    return make_float2(u.x + v.x, u.y + v.y);
   }
   __device__ void tile(uint32_t tmem_acc, int batch, int m0, int) {
     const int r = m0 + epi_row();
@@ -520,27 +585,37 @@ struct EpiLayerNorm {
     const long grow = static_cast<long>(batch) * s.M + r;
     const int c_begin = epi_half() * (BLOCK_N / 64);
     const int c_end = c_begin + BLOCK_N / 64;
-    float sum = 0.f;
+    // one pass over the accumulator for both moments (biased variance E[x^2] - mean^2 in fp32: the normalised inputs
+    // are O(1) with |mean| << 1 + std, so the cancellation costs < 1e-6 relative), shifted by the row's first value
+    float sum = 0.f, sq = 0.f, shift = 0.f;
 #pragma unroll 1
     for (int c = c_begin; c < c_end; ++c) {
       float x[32];
       load_acc32(tmem_acc, c * 32, x);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) sum += x[j];
-    }
-    const float mean = row_total(sum * p.acc_scale) * (1.f / BLOCK_N);
-    float sq = 0.f;
-#pragma unroll 1
-    for (int c = c_begin; c < c_end; ++c) {
-      float x[32];
-      load_acc32(tmem_acc, c * 32, x);
+      if (c == c_begin) shift = x[0] * p.acc_scale;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float d = x[j] * p.acc_scale - mean;
-        sq += d * d;
+        const float d = x[j] * p.acc_scale - shift;
+        sum += d;
+        sq = fmaf(d, d, sq);
       }
     }
-    const float rstd = rsqrtf(row_total(sq) * (1.f / BLOCK_N) + p.eps);
+    // both column halves must use the same shift: re-centre the right half's moments onto the left half's shift
+    float* sh_shift = s_red + 2 * 128 * 2;   // [128] behind the float2 exchange area
+    if (epi_half() == 0) sh_shift[epi_row()] = shift;
+    epi_bar_sync();
+    {
+      const float delta = shift - sh_shift[epi_row()];     // 0 for the left half
+      const float n = static_cast<float>(BLOCK_N / 2);
+      sq = sq + 2.f * delta * sum + n * delta * delta;       // sum (d + delta)^2
+      sum = sum + n * delta;
+      shift -= delta;
+    }
+    const float2 tot = row_total2(sum, sq);
+    const float m1 = tot.x * (1.f / BLOCK_N);
+    const float mean = shift + m1;
+    const float var = fmaxf(tot.y * (1.f / BLOCK_N) - m1 * m1, 0.f);
+    const float rstd = rsqrtf(var + p.eps);
 #pragma unroll 1
     for (int c = c_begin; c < c_end; ++c) {
       float x[32];
@@ -596,6 +671,7 @@ struct EpiPlanes {
   __device__ EpiPlanes(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_), scr(epi_scratch(smem)) {}
   __device__ void item_begin(int, int, int) {}
   __device__ void item_end(int, int, int) {}
+  __device__ void prefetch(int, int, int) {}
   __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
     const int r = m0 + epi_row();
     const bool row_ok = r < s.M;
@@ -678,6 +754,39 @@ struct EpiConv {
   }
   __device__ void item_begin(int, int, int) {}
   __device__ void item_end(int, int, int) {}
+  // residual / FPN-upsample source rows of this thread's pixel -> L2, issued while the tile's MMAs still run
+  __device__ void prefetch(int batch, int m0, int n0) {
+    if (!p.res_hi && !p.up_hi) return;
+    const int row = epi_row();
+    const int mt = m0 / kBlockM;
+    const int ty = mt / p.tiles_w, tx = mt - ty * p.tiles_w;
+    const int y = ty * kConvTileH + row / kConvTileW;
+    const int x = tx * kConvTileW + row % kConvTileW;
+    if (y >= p.H_out || x >= p.W_out) return;
+    const int c_lo = n0 + (epi_half() == 0 ? 0 : kChunksHalf0) * 32;
+    const int c_hi = min(n0 + (epi_half() == 0 ? kChunksHalf0 : kChunks) * 32, s.N);
+    if (p.res_hi) {
+      const long pix = (static_cast<long>(batch) * p.H_out + y) * p.W_out + x;
+      for (int c = c_lo; c < c_hi; c += 64) {
+        prefetch_l2(p.res_hi + pix * p.res_ld + c);
+        prefetch_l2(p.res_lo + pix * p.res_ld + c);
+      }
+    }
+    if (p.up_hi) {
+      const float sh = p.H_out > 1 ? static_cast<float>(p.up_h - 1) / static_cast<float>(p.H_out - 1) : 0.f;
+      const float sw = p.W_out > 1 ? static_cast<float>(p.up_w - 1) / static_cast<float>(p.W_out - 1) : 0.f;
+      const int y0 = static_cast<int>(sh * y), x0 = static_cast<int>(sw * x);
+      const int y1 = y0 + (y0 < p.up_h - 1 ? 1 : 0), x1 = x0 + (x0 < p.up_w - 1 ? 1 : 0);
+      const long base = static_cast<long>(batch) * p.up_h * p.up_w;
+      const long u[4] = {(base + static_cast<long>(y0) * p.up_w + x0) * p.up_ld, (base + static_cast<long>(y0) * p.up_w + x1) * p.up_ld,
+                         (base + static_cast<long>(y1) * p.up_w + x0) * p.up_ld, (base + static_cast<long>(y1) * p.up_w + x1) * p.up_ld};
+      for (int q = 0; q < 4; ++q)
+        for (int c = c_lo; c < c_hi; c += 64) {
+          prefetch_l2(p.up_hi + u[q] + c);
+          prefetch_l2(p.up_lo + u[q] + c);
+        }
+    }
+  }
   __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
     const int t = epi_tid();
     for (int j = t; j < kCols; j += kEpiThreads) {
@@ -860,6 +969,7 @@ struct EpiScoreLse {
     s_cmax = reinterpret_cast<float*>(smem + BLOCK_N * 4 + 4 * BLOCK_N * 8);
     s_rmerge = reinterpret_cast<float2*>(smem + BLOCK_N * 4 + 4 * BLOCK_N * 8 + 8 * 32 * 4);
   }
+  __device__ void prefetch(int, int, int) {}
   __device__ void item_begin(int, int, int) {
     row_m = kNegBig;
     row_l = 0.f;
@@ -1016,6 +1126,7 @@ struct EpiConfStore {
   }
   __device__ void item_begin(int, int, int) {}
   __device__ void item_end(int, int, int) {}
+  __device__ void prefetch(int, int, int) {}
   __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
     const int t = epi_tid();
     for (int j = t; j < BLOCK_N; j += kEpiThreads) {
@@ -1087,6 +1198,7 @@ struct EpiScoreArgmax {
     s_cpart = reinterpret_cast<unsigned long long*>(smem + BLOCK_N * 4);
     s_rmerge = reinterpret_cast<ArgPart*>(smem + BLOCK_N * 4 + 4 * BLOCK_N * 8);
   }
+  __device__ void prefetch(int, int, int) {}
   __device__ void item_begin(int, int, int) {
     best_key = -3.0e38f;
     best_j = -1;

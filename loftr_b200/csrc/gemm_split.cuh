@@ -122,6 +122,8 @@ struct AccLayout {
 //   static constexpr int kSmemBytes;             // extra dynamic smem the epilogue wants
 //   __device__ Epi(const Params&, uint8_t* smem, const GemmShape&);
 //   __device__ void item_begin(int batch, int m0, int chunk);
+//   __device__ void prefetch(int batch, int m0, int n0);   // called BEFORE the wait for the tile's accumulator: the
+//                                                          // place to pull residual / bias data towards L2
 //   __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0);   // tmem_acc: column base of this
 //                                                                         // tile's accumulator (lane field 0)
 //   __device__ void item_end(int batch, int m0, int chunk);
@@ -137,8 +139,10 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   constexpr int kCluster = kMode == 0 ? 1 : 2;
   using S = GemmSmem<BLOCK_N, kPair>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // Dynamic smem base is only guaranteed 16B aligned; the swizzled tiles need 1024B.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // Dynamic smem base is only guaranteed 16B aligned; the swizzled tiles need 1024B.  The padding is applied as
+  // pointer arithmetic on the __shared__ array (NOT through an integer round trip): the compiler must keep seeing
+  // shared-space pointers, otherwise every epilogue smem access becomes a generic LD/ST (measured: stall_lg, 3x slower).
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = smem;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kRingBytes);
   uint64_t* empty_bar = full_bar + S::kStages;
@@ -423,6 +427,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
       const bool real = mt < shape.m_tiles;   // phantom row tile of an odd tail: consume, emit nothing
       if (real) epi.item_begin(batch, mt * kBlockM, chunk);
       for (int nt = nt_begin; nt < nt_end; ++nt) {
+        if (real) epi.prefetch(batch, mt * kBlockM, nt * BLOCK_N);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         if (real) epi.tile(tmem_base + acc * AL::kColsPerStage, batch, mt * kBlockM, nt * BLOCK_N);

@@ -134,6 +134,10 @@ __device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMa
       : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // ---------------------------------------------------------------- cluster
 // arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
