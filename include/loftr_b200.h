@@ -235,6 +235,13 @@ typedef struct LbFineMatchArgs {
 
 int lb_fine_match(const LbFineMatchArgs* args /*host*/, void* stream);
 
+/* ---- evaluation harness.  Squared symmetric epipolar distance of every match against the
+ * ground-truth relative pose of its pair: replaces compute_symmetrical_epipolar_errors / symmetric_epipolar_distance
+ * (src/utils/metrics.py:30-72).  T_0to1 [n_pairs,4,4], K0 / K1 [n_pairs,3,3] fp32 row-major, m_bids[m] = pair of
+ * match m; epi_errs [M] out. */
+int lb_epipolar_errors(const float* mkpts0_f, const float* mkpts1_f, const long long* m_bids, long M, int n_pairs,
+                       const float* T_0to1, const float* K0, const float* K1, float* epi_errs, void* stream);
+
 /* ---- multi-GPU: all-gather of the match lists.  Pairs are sharded over ranks (one process per GPU); every rank ends
  * with the global list.  Replaces the reference's gather() (src/utils/comm.py:113-176, called from
  * src/lightning/lightning_loftr.py:235,241: a size exchange plus a padded pickled-object all_gather on a gloo side

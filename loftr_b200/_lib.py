@@ -119,6 +119,8 @@ SIGNATURES = {
     "lb_fine_preprocess_workspace_bytes": (c_size_t, [c_long, c_int, c_int]),
     "lb_fine_preprocess": (c_int, [C.POINTER(LbFinePreprocessArgs), c_void_p, c_size_t, c_void_p]),
     "lb_fine_match": (c_int, [C.POINTER(LbFineMatchArgs), c_void_p]),
+    "lb_epipolar_errors": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p]),
     "lb_comm_unique_id": (c_int, [C.c_char_p, C.c_char_p]),
     "lb_comm_init": (c_int, [C.c_char_p, c_int, c_int, c_int, C.c_char_p, C.POINTER(c_void_p)]),
     "lb_comm_destroy": (c_int, [c_void_p]),

@@ -180,6 +180,22 @@ static int make_map_nhwc(CUtensorMap* m, const void* base, int C, int W, int H, 
   return 0;
 }
 
+// fp32 output [batches][rows][cols] (row stride ld elements) for TMA stores: box 32 x 32 x 1, 128-byte swizzle.
+static int make_out_map_f32(CUtensorMap* m, const float* base, long cols, long rows, long batches, long ld) {
+  auto enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 4) % 16 != 0) return fail("output not 16-byte aligned");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batches)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld * 4), static_cast<cuuint64_t>(rows * ld * 4)};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (output) failed with CUresult %d", static_cast<int>(r));
+  return 0;
+}
+
 struct Planes {
   const void* hi;
   const void* lo;
@@ -593,17 +609,17 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
     if (self_pass) {
       Planes A{cat_hi + x_base * ldc, cat_lo + x_base * ldc, ldc, 0};
       Planes B{lw.wqkv_hi, lw.wqkv_lo, C, 0};
-      typename Epi::Params ep{w.qkv + x_base * 3 * C, 3 * C, 2 * C, mask ? mask + x_base : nullptr, lw.s_qkv, 0};
+      typename Epi::Params ep{w.qkv + x_base * 3 * C, 3 * C, 2 * C, mask ? mask + x_base : nullptr, lw.s_qkv, 0, CUtensorMap{}};
       LB_TRY((launch_gemm<BN, Epi>(TAG_PROJ, A, B, 1, static_cast<int>(x_rows), 3 * C, C, 0, ep, stream)));
     } else {
       Planes Aq{cat_hi + x_base * ldc, cat_lo + x_base * ldc, ldc, 0};
       Planes Bq{lw.wqkv_hi, lw.wqkv_lo, C, 0};
-      typename Epi::Params eq{w.qkv + x_base * 3 * C, 3 * C, C, mask ? mask + x_base : nullptr, lw.s_qkv, 0};
+      typename Epi::Params eq{w.qkv + x_base * 3 * C, 3 * C, C, mask ? mask + x_base : nullptr, lw.s_qkv, 0, CUtensorMap{}};
       LB_TRY((launch_gemm<BN, Epi>(TAG_PROJ, Aq, Bq, 1, static_cast<int>(x_rows), C, C, 0, eq, stream)));
       Planes Ak{cat_hi + s_base * ldc, cat_lo + s_base * ldc, ldc, 0};
       Planes Bk{static_cast<const __half*>(lw.wqkv_hi) + static_cast<long>(C) * C,
                 static_cast<const __half*>(lw.wqkv_lo) + static_cast<long>(C) * C, C, 0};
-      typename Epi::Params ek{w.qkv + s_base * 3 * C + C, 3 * C, C, mask ? mask + s_base : nullptr, lw.s_qkv, 0};
+      typename Epi::Params ek{w.qkv + s_base * 3 * C + C, 3 * C, C, mask ? mask + s_base : nullptr, lw.s_qkv, 0, CUtensorMap{}};
       LB_TRY((launch_gemm<BN, Epi>(TAG_PROJ, Ak, Bk, 1, static_cast<int>(s_rows), 2 * C, C, 0, ek, stream)));
     }
   }
@@ -867,13 +883,16 @@ int lb_gemm_split(const void* a_hi, const void* a_lo, long lda, long a_batch_str
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const char* pe = getenv("LOFTR_B200_PROBE_NULL_EPI");   // measurement probe of the main loop (tools/gemm_probe.py)
   const int skip = pe ? atoi(pe) : 0;
+  CUtensorMap tm_out;
+  memset(&tm_out, 0, sizeof(tm_out));
+  if (skip == 3) LB_TRY(make_out_map_f32(&tm_out, out, N, M, batches, ldo));
   if (N % 256 == 0 || N > 128) {
     using Epi = EpiActStore<256>;
-    Epi::Params ep{out, static_cast<int>(ldo), 0, nullptr, 1.f, skip};
+    Epi::Params ep{out, static_cast<int>(ldo), 0, nullptr, 1.f, skip, tm_out};
     return launch_gemm<256, Epi>(TAG_GEMM_TEST, A, B, batches, M, N, K, 0, ep, st);
   }
   using Epi = EpiActStore<128>;
-  Epi::Params ep{out, static_cast<int>(ldo), 0, nullptr, 1.f, skip};
+  Epi::Params ep{out, static_cast<int>(ldo), 0, nullptr, 1.f, skip, tm_out};
   return launch_gemm<128, Epi>(TAG_GEMM_TEST, A, B, batches, M, N, K, 0, ep, st);
 }
 
@@ -1324,6 +1343,21 @@ int lb_fine_match(const LbFineMatchArgs* a, void* stream) {
   p.mkpts1_c = a->mkpts1_c; p.expec_f = a->expec_f; p.mkpts1_f = a->mkpts1_f;
   const int warps_per_block = 8;
   fine_match_kernel<<<cdiv(a->M, warps_per_block), warps_per_block * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  LB_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ evaluation
+int lb_epipolar_errors(const float* mkpts0_f, const float* mkpts1_f, const long long* m_bids, long M, int n_pairs,
+                       const float* T_0to1, const float* K0, const float* K1, float* epi_errs, void* stream) {
+  if (M <= 0) return 0;
+  DeviceGuard dev_guard;
+  LB_TRY(dev_guard.bind(epi_errs));
+  int sms;
+  LB_TRY(device_check(&sms));
+  if (!mkpts0_f || !mkpts1_f || !m_bids || !T_0to1 || !K0 || !K1) return fail("lb_epipolar_errors: null input");
+  epipolar_error_kernel<<<cdiv(M, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(mkpts0_f, mkpts1_f, m_bids, M, n_pairs,
+                                                                                      T_0to1, K0, K1, epi_errs);
   LB_LAUNCHED();
   return 0;
 }

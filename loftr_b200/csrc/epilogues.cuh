@@ -253,13 +253,18 @@ struct EpiActStore {
     int elu_cols;            // columns [0, elu_cols) get elu+1
     const uint8_t* rowmask;  // optional [batches*M] (1 = valid)
     float acc_scale;         // 2^-e: undoes the power-of-two pre-scaling of the weight planes (exact)
-    int skip;                // probe mode (LOFTR_B200_PROBE_NULL_EPI=1, lb_gemm_split only): 1 = drain nothing, 2 = TMEM loads only
+    int skip;                // probe mode (LOFTR_B200_PROBE_NULL_EPI, lb_gemm_split only): 1 = drain nothing, 2 = TMEM loads only,
+                             // 3 = TMA-store epilogue (tm_out)
+    CUtensorMap tm_out;      // fp32 [batches][M][N], box 32 x 32, 128-byte swizzle (mode 3)
   };
-  static constexpr int kSmemBytes = kEpiScratchBytes;
+  static constexpr int kSmemBytes = 8 * 4096;   // per-warp 32 x 128 B staging tile (TMA store) / 2 KB transposer scratch
   const Params& p;
   const GemmShape& s;
   uint32_t* scr;
-  __device__ EpiActStore(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_), scr(epi_scratch(smem)) {}
+  uint8_t* stage;
+  __device__ EpiActStore(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_), scr(epi_scratch(smem)) {
+    stage = smem + ((epi_tid() >> 5) << 12);
+  }
   __device__ void item_begin(int, int, int) {}
   __device__ void item_end(int, int, int) {}
   __device__ void prefetch(int, int, int) {}
@@ -292,6 +297,24 @@ struct EpiActStore {
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] *= mk;
+      if (p.skip == 3) {
+        // TMA-store epilogue: stage the warp's 32 x 32 fp32 block (128-byte rows, 16-byte chunk q of row r at
+        // q ^ (r & 7) = the 128B swizzle) and let the copy engine write it; rows past M are clipped by the tensor map
+        const int lane = threadIdx.x & 31;
+        if (lane == 0) tma_store_wait_read();          // the previous block of this warp has left the staging tile
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(stage + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+              make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&p.tm_out, stage, col, m0 + ((epi_tid() >> 5) & 3) * 32, batch);
+          tma_store_commit();
+        }
+        continue;
+      }
       warp_store_f32x32(scr, row_ok ? p.out + grow * p.ld + col : nullptr, x);
     }
   }

@@ -89,7 +89,7 @@ struct GemmSmem {
   static constexpr int kStageBytes = 2 * kATile + 2 * kBTile;                // hi + lo of A and B
   static constexpr int kStages = (192 * 1024) / kStageBytes;                 // 2 (96 KB) / 3 (64 KB) / 4 (48 KB)
   static constexpr int kRingBytes = kStages * kStageBytes;
-  static constexpr int kBarBytes = 256;
+  static constexpr int kBarBytes = 1024;   // barriers + TMEM slot; keeps the epilogue area 1024-byte aligned (TMA-store staging)
 };
 
 // TMEM layout.  kDual: the two correction products (hi*lo, lo*hi) accumulate into a SECOND accumulator that the
@@ -133,7 +133,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                   const __grid_constant__ CUtensorMap tm_ar_hi, const __grid_constant__ CUtensorMap tm_ar_lo,
                   const __grid_constant__ CUtensorMap tm_br_hi, const __grid_constant__ CUtensorMap tm_br_lo,
-                  const GemmShape shape, const typename Epi::Params epi_params) {
+                  const GemmShape shape, const __grid_constant__ typename Epi::Params epi_params) {
   constexpr bool kPair = kMode == 2;
   constexpr bool kMcast = kMode == 1;
   constexpr int kCluster = kMode == 0 ? 1 : 2;
@@ -445,6 +445,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
       }
       if (real) epi.item_end(batch, mt * kBlockM, chunk);
     }
+    tma_store_wait_all();   // bulk stores issued by this thread (if any) have landed before the CTA may exit
   }
 
   tc_fence_before();

@@ -806,6 +806,44 @@ __global__ void fine_match_kernel(const FineMatchParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Evaluation harness: squared symmetric epipolar distance of every match against the
+// ground-truth relative pose of its pair (reference src/utils/metrics.py:30-72): E = [t]_x R from T_0to1, points
+// normalised by the intrinsics, d = (p1^T E p0)^2 (1 / |(E p0)_xy|^2 + 1 / |(E^T p1)_xy|^2).  One thread per match.
+__global__ void epipolar_error_kernel(const float* __restrict__ mk0, const float* __restrict__ mk1,
+                                      const long long* __restrict__ bids, long M, int n_pairs,
+                                      const float* __restrict__ T_0to1 /*[n,4,4]*/, const float* __restrict__ K0 /*[n,3,3]*/,
+                                      const float* __restrict__ K1, float* __restrict__ err) {
+  const long m = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (m >= M) return;
+  const long b = bids[m];
+  if (b < 0 || b >= n_pairs) {
+    err[m] = __int_as_float(0x7fc00000);   // NaN: a match that belongs to no pair
+    return;
+  }
+  const float* T = T_0to1 + b * 16;
+  const float tx = T[3], ty = T[7], tz = T[11];
+  float E[9];   // [t]_x R, row-major
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float r0 = T[c], r1 = T[4 + c], r2 = T[8 + c];
+    E[c] = -tz * r1 + ty * r2;
+    E[3 + c] = tz * r0 - tx * r2;
+    E[6 + c] = -ty * r0 + tx * r1;
+  }
+  const float* k0 = K0 + b * 9;
+  const float* k1 = K1 + b * 9;
+  const float x0 = (mk0[2 * m] - k0[2]) / k0[0], y0 = (mk0[2 * m + 1] - k0[5]) / k0[4];
+  const float x1 = (mk1[2 * m] - k1[2]) / k1[0], y1 = (mk1[2 * m + 1] - k1[5]) / k1[4];
+  const float a0 = E[0] * x0 + E[1] * y0 + E[2];          // E p0
+  const float a1 = E[3] * x0 + E[4] * y0 + E[5];
+  const float a2 = E[6] * x0 + E[7] * y0 + E[8];
+  const float c0 = E[0] * x1 + E[3] * y1 + E[6];          // E^T p1
+  const float c1 = E[1] * x1 + E[4] * y1 + E[7];
+  const float pep = x1 * a0 + y1 * a1 + a2;
+  err[m] = pep * pep * (1.0f / (a0 * a0 + a1 * a1) + 1.0f / (c0 * c0 + c1 * c1));
+}
+
 // Second version of the stem: two horizontally adjacent output pixels per thread share every weight fetch
 // (7 x 9 input patch in registers), halving the shared-memory reads per FMA.
 template <int COUT>

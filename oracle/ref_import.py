@@ -3,7 +3,9 @@ generation -- TEST INFRASTRUCTURE, only usable in the authoring container (the G
 
 The reference needs three modules that are not installed / not shipped:
   * kornia (pinned 0.4.1): only `dsnt.spatial_expectation2d` and `create_meshgrid` are on the hot path
-    (fine_matching.py:5-6,49-50) -> 10-line stand-ins with the documented semantics.
+    (fine_matching.py:5-6,49-50) -> 10-line stand-ins with the documented semantics; the evaluation metrics
+    (src/utils/metrics.py:6-7) additionally use `epipolar.numeric.cross_product_matrix` and
+    `conversions.convert_points_to_homogeneous` -> two more stand-ins.
   * yacs: `CfgNode` is used as an attribute dict (cvpr_ds_config.py:1-9) -> a dict subclass.
   * src/loftr/utils/superglue.py: deliberately absent from the reference (README.md:63-74); the pinned
     submodule copy third_party/SuperGluePretrainedNetwork/models/superglue.py is registered under that
@@ -47,8 +49,23 @@ def _install_stubs():
             ey = (flat * py).sum(-1, keepdim=True)
             return torch.cat([ex, ey], -1)  # [B, N, 2]
 
+        def cross_product_matrix(x):   # kornia.geometry.epipolar.numeric: [..., 3] -> [..., 3, 3] skew-symmetric
+            z = torch.zeros_like(x[..., 0])
+            return torch.stack([torch.stack([z, -x[..., 2], x[..., 1]], -1), torch.stack([x[..., 2], z, -x[..., 0]], -1),
+                                torch.stack([-x[..., 1], x[..., 0], z], -1)], -2)
+
+        def convert_points_to_homogeneous(points):   # kornia.geometry.conversions: append a 1
+            return torch.nn.functional.pad(points, [0, 1], "constant", 1.0)
+
         kornia = types.ModuleType("kornia")
         geometry = types.ModuleType("kornia.geometry")
+        epipolar = types.ModuleType("kornia.geometry.epipolar")
+        numeric = types.ModuleType("kornia.geometry.epipolar.numeric")
+        conversions = types.ModuleType("kornia.geometry.conversions")
+        numeric.cross_product_matrix = cross_product_matrix
+        epipolar.numeric = numeric
+        conversions.convert_points_to_homogeneous = convert_points_to_homogeneous
+        geometry.epipolar, geometry.conversions = epipolar, conversions
         subpix = types.ModuleType("kornia.geometry.subpix")
         dsnt = types.ModuleType("kornia.geometry.subpix.dsnt")
         utils = types.ModuleType("kornia.utils")
@@ -60,6 +77,9 @@ def _install_stubs():
         utils.grid = grid
         utils.create_meshgrid = create_meshgrid
         kornia.geometry, kornia.utils = geometry, utils
+        for name, mod in [("kornia.geometry.epipolar", epipolar), ("kornia.geometry.epipolar.numeric", numeric),
+                          ("kornia.geometry.conversions", conversions)]:
+            sys.modules[name] = mod
         for name, mod in [("kornia", kornia), ("kornia.geometry", geometry), ("kornia.geometry.subpix", subpix),
                           ("kornia.geometry.subpix.dsnt", dsnt), ("kornia.utils", utils), ("kornia.utils.grid", grid)]:
             sys.modules[name] = mod
@@ -103,3 +123,15 @@ def load_reference():
         spec.loader.exec_module(mod)
     import src.loftr as ref
     return ref
+
+
+def load_reference_metrics():
+    """The reference's src/utils/metrics.py module (evaluation harness; needs cv2 and loguru, both installed)."""
+    load_reference()
+    import numpy as np
+    if not hasattr(np, "bool"):       # metrics.py:128 uses the alias removed in numpy 1.24
+        np.bool = bool
+    if not hasattr(np, "trapz"):      # metrics.py:159; numpy >= 2.4 drops it
+        np.trapz = np.trapezoid
+    import src.utils.metrics as m
+    return m

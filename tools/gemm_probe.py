@@ -15,14 +15,15 @@ from loftr_b200.loftr import split_planes, _stream  # noqa: E402
 lib = _lib.load()
 dev = "cuda:0"
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for (m, n, k) in [(76800, 256, 256), (76800, 768, 256), (76800, 512, 512), (76800, 256, 512), (38400, 256, 256)]:
+for (m, n, k) in [(76800, 256, 256), (76800, 768, 256), (76800, 512, 512), (76800, 256, 512), (38400, 256, 256), (4800 * 3 + 77, 256, 256)]:
     a = torch.randn(m, k, device=dev)
     w = torch.randn(n, k, device=dev)
     ah, al = split_planes(a)
     wh, wl = split_planes(w)
     out = torch.empty(m, n, dtype=torch.float32, device=dev)
     res = {}
-    for mode, name in ((0, "store"), (2, "tmem_ld_only"), (1, "null")):
+    outs = {}
+    for mode, name in ((0, "store"), (3, "tma_store"), (2, "tmem_ld_only"), (1, "null")):
         os.environ["LOFTR_B200_PROBE_NULL_EPI"] = str(mode)
         ts = []
         for it in range(6):
@@ -36,6 +37,10 @@ for (m, n, k) in [(76800, 256, 256), (76800, 768, 256), (76800, 512, 512), (7680
             if it >= 2:
                 ts.append(e0.elapsed_time(e1))
         res[name] = sum(ts) / len(ts)
+        if mode in (0, 3):
+            outs[mode] = out.clone()
+            out.zero_()
+    same = torch.equal(outs[0], outs[3])
     fl = 2.0 * m * n * k * 3
-    print(f"M={m} N={n} K={k}: " + "  ".join(f"{kk} {v * 1e3:7.1f} us ({fl / v / 1e9:6.0f} TF/s issued)" for kk, v in res.items()), flush=True)
+    print(f"M={m} N={n} K={k}: " + "  ".join(f"{kk} {v * 1e3:7.1f} us ({fl / v / 1e9:6.0f} TF/s issued)" for kk, v in res.items()) + f"  tma==plain: {same}", flush=True)
 os.environ["LOFTR_B200_PROBE_NULL_EPI"] = "0"
