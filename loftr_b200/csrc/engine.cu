@@ -180,19 +180,66 @@ static int make_map_nhwc(CUtensorMap* m, const void* base, int C, int W, int H, 
   return 0;
 }
 
-// fp32 output [batches][rows][cols] (row stride ld elements) for TMA stores: box 32 x 32 x 1, 128-byte swizzle.
-static int make_out_map_f32(CUtensorMap* m, const float* base, long cols, long rows, long batches, long ld) {
+// ---- output tensor maps for the TMA-store epilogues (epilogues.cuh OutMaps).  LOFTR_B200_TMA_STORE=0 disables them
+// (the epilogues then use their pointer-based store paths) for A/B measurements.
+static bool use_tma_store() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LOFTR_B200_TMA_STORE");
+    v = e ? (atoi(e) != 0 ? 1 : 0) : 1;
+  }
+  return v == 1;
+}
+// [batches][rows][cols] matrix (row stride ld, batch stride bs elements; bs = 0 -> rows * ld): box 32 x 32 x 1,
+// 64-byte swizzle for fp16 planes, 128-byte swizzle for fp32
+static int make_out_map(CUtensorMap* m, const void* base, bool f32, long cols, long rows, long batches, long ld, long bs) {
   auto enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 4) % 16 != 0) return fail("output not 16-byte aligned");
+  const int esz = f32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * esz) % 16 != 0 || (bs * esz) % 16 != 0)
+    return fail("TMA-store output not 16-byte aligned");
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batches)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld * 4), static_cast<cuuint64_t>(rows * ld * 4)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld * esz), static_cast<cuuint64_t>((bs > 0 ? bs : rows * ld) * esz)};
   cuuint32_t box[3] = {32, 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (output) failed with CUresult %d", static_cast<int>(r));
+  return 0;
+}
+// NHWC [N][H][W][C] (pixel stride ld elements): box 32 channels x 16 x 2 pixels x 1 image
+static int make_out_map_nhwc(CUtensorMap* m, const void* base, bool f32, int C, int W, int H, int N, long ld) {
+  auto enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+  const int esz = f32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * esz) % 16 != 0) return fail("TMA-store NHWC output not 16-byte aligned");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(ld * esz), static_cast<cuuint64_t>(ld * esz) * W,
+                           static_cast<cuuint64_t>(ld * esz) * W * H};
+  cuuint32_t box[4] = {32, static_cast<cuuint32_t>(kConvTileW), 2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (NHWC output) failed with CUresult %d", static_cast<int>(r));
+  return 0;
+}
+// planes (+ optional fp32) of a [batches][rows][cols] output
+static int fill_out_maps(OutMaps* om, const void* hi, const void* lo, long ld_pl, const float* f32, long ld_f32, long cols,
+                         long rows, long batches) {
+  memset(om, 0, sizeof(*om));
+  om->dims = 3;
+  if (!use_tma_store()) return 0;
+  if (hi) {
+    LB_TRY(make_out_map(&om->hi, hi, false, cols, rows, batches, ld_pl, 0));
+    LB_TRY(make_out_map(&om->lo, lo, false, cols, rows, batches, ld_pl, 0));
+    om->use |= 1;
+  }
+  if (f32) {
+    LB_TRY(make_out_map(&om->f32, f32, true, cols, rows, batches, ld_f32, 0));
+    om->use |= 2;
+  }
   return 0;
 }
 
@@ -260,7 +307,7 @@ static int launch_raw(int tag, const GemmMaps& maps, const GemmShape& s, const t
                       cudaStream_t st) {
   constexpr int kCluster = kMode == 0 ? 1 : 2;
   using S = GemmSmem<BN, kMode == 2>;
-  constexpr int smem_bytes = S::kRingBytes + S::kBarBytes + Epi::kSmemBytes + 1024;
+  constexpr int smem_bytes = S::kRingBytes + S::kBarBytes + Epi::kSmemBytes;
   static_assert(smem_bytes <= 232448, "shared memory budget exceeded");
   auto kern = gemm_split_kernel<BN, Epi, kDual, kMode>;
   static bool configured[kMaxDevices] = {false};  // per instantiation and device
@@ -535,12 +582,27 @@ static int run_conv(const ConvRun& r, int N, cudaStream_t st) {
   Planes in{r.in.hi, r.in.lo, r.in.ld, 0};
   Planes wg{w.w_hi, w.w_lo, static_cast<long>(taps) * cin_blocks * kBlockK, 0};
   Planes wr{w.wr_hi, w.wr_lo, static_cast<long>(taps) * kRemChannels, 0};
+  // NHWC output maps of the TMA-store epilogue (planes and / or fp32 feature map)
+  OutMaps om;
+  memset(&om, 0, sizeof(om));
+  om.dims = 4;
+  if (use_tma_store()) {
+    if (r.out) {
+      LB_TRY(make_out_map_nhwc(&om.hi, r.out->hi, false, d.Cout, d.W_out, d.H_out, N, r.out->ld));
+      LB_TRY(make_out_map_nhwc(&om.lo, r.out->lo, false, d.Cout, d.W_out, d.H_out, N, r.out->ld));
+      om.use |= 1;
+    }
+    if (r.out_f32) {
+      LB_TRY(make_out_map_nhwc(&om.f32, r.out_f32, true, d.Cout, d.W_out, d.H_out, N, r.f32_ld));
+      om.use |= 2;
+    }
+  }
 #define LB_CONV_CASE(BN)                                                                                              \
   {                                                                                                                   \
     EpiConv<BN>::Params ep{w.scale, w.shift, r.act, r.res ? r.res->hi : nullptr, r.res ? r.res->lo : nullptr,       \
                            r.res ? r.res->ld : 0, r.up ? r.up->hi : nullptr, r.up ? r.up->lo : nullptr,              \
                            r.up ? r.up->ld : 0, r.up_h, r.up_w, r.out ? r.out->hi : nullptr,                          \
-                           r.out ? r.out->lo : nullptr, r.out ? r.out->ld : 0, r.out_f32, r.f32_ld, 0, 0, 0};         \
+                           r.out ? r.out->lo : nullptr, r.out ? r.out->ld : 0, r.out_f32, r.f32_ld, 0, 0, 0, om};     \
     return launch_conv<BN>(in, wg, wr, d, ep, st);                                                                    \
   }
   // output-channel tile: the smallest built N that covers Cout (196 -> 208: 13 x 16, no MMAs on 60 padding columns)
@@ -609,17 +671,22 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
     if (self_pass) {
       Planes A{cat_hi + x_base * ldc, cat_lo + x_base * ldc, ldc, 0};
       Planes B{lw.wqkv_hi, lw.wqkv_lo, C, 0};
-      typename Epi::Params ep{w.qkv + x_base * 3 * C, 3 * C, 2 * C, mask ? mask + x_base : nullptr, lw.s_qkv, 0, CUtensorMap{}};
+      OutMaps om;
+      LB_TRY(fill_out_maps(&om, nullptr, nullptr, 0, w.qkv + x_base * 3 * C, 3 * C, 3 * C, x_rows, 1));
+      typename Epi::Params ep{w.qkv + x_base * 3 * C, 3 * C, 2 * C, mask ? mask + x_base : nullptr, lw.s_qkv, 0, om};
       LB_TRY((launch_gemm<BN, Epi>(TAG_PROJ, A, B, 1, static_cast<int>(x_rows), 3 * C, C, 0, ep, stream)));
     } else {
       Planes Aq{cat_hi + x_base * ldc, cat_lo + x_base * ldc, ldc, 0};
       Planes Bq{lw.wqkv_hi, lw.wqkv_lo, C, 0};
-      typename Epi::Params eq{w.qkv + x_base * 3 * C, 3 * C, C, mask ? mask + x_base : nullptr, lw.s_qkv, 0, CUtensorMap{}};
+      OutMaps omq, omk;
+      LB_TRY(fill_out_maps(&omq, nullptr, nullptr, 0, w.qkv + x_base * 3 * C, 3 * C, C, x_rows, 1));
+      LB_TRY(fill_out_maps(&omk, nullptr, nullptr, 0, w.qkv + s_base * 3 * C + C, 3 * C, 2 * C, s_rows, 1));
+      typename Epi::Params eq{w.qkv + x_base * 3 * C, 3 * C, C, mask ? mask + x_base : nullptr, lw.s_qkv, 0, omq};
       LB_TRY((launch_gemm<BN, Epi>(TAG_PROJ, Aq, Bq, 1, static_cast<int>(x_rows), C, C, 0, eq, stream)));
       Planes Ak{cat_hi + s_base * ldc, cat_lo + s_base * ldc, ldc, 0};
       Planes Bk{static_cast<const __half*>(lw.wqkv_hi) + static_cast<long>(C) * C,
                 static_cast<const __half*>(lw.wqkv_lo) + static_cast<long>(C) * C, C, 0};
-      typename Epi::Params ek{w.qkv + s_base * 3 * C + C, 3 * C, C, mask ? mask + s_base : nullptr, lw.s_qkv, 0, CUtensorMap{}};
+      typename Epi::Params ek{w.qkv + s_base * 3 * C + C, 3 * C, C, mask ? mask + s_base : nullptr, lw.s_qkv, 0, omk};
       LB_TRY((launch_gemm<BN, Epi>(TAG_PROJ, Ak, Bk, 1, static_cast<int>(s_rows), 2 * C, C, 0, ek, stream)));
     }
   }
@@ -659,9 +726,12 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
     using Epi = EpiLayerNorm<BN>;
     Planes A{w.att_hi + x_base * C, w.att_lo + x_base * C, C, 0};
     Planes B{lw.wm_hi, lw.wm_lo, C, 0};
+    OutMaps om;
+    LB_TRY(fill_out_maps(&om, static_cast<__half*>(st.cat_hi) + x_base * ldc + C, static_cast<__half*>(st.cat_lo) + x_base * ldc + C,
+                         ldc, nullptr, 0, C, x_rows, 1));
     typename Epi::Params ep{lw.ln1_g, lw.ln1_b, 1e-5f, nullptr, 0, nullptr, nullptr, 0, nullptr, 0,
                             static_cast<__half*>(st.cat_hi) + x_base * ldc,
-                            static_cast<__half*>(st.cat_lo) + x_base * ldc, static_cast<int>(ldc), C, lw.s_m};
+                            static_cast<__half*>(st.cat_lo) + x_base * ldc, static_cast<int>(ldc), C, lw.s_m, om};
     LB_TRY((launch_gemm<BN, Epi>(TAG_MERGE_LN, A, B, 1, static_cast<int>(x_rows), C, C, 0, ep, stream)));
   }
   // 5. mlp[0] + ReLU on cat([x, message]) -> h planes           [transformer.py:55, mlp 22-26]
@@ -669,8 +739,10 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
     using Epi = EpiPlanes<BN>;
     Planes A{cat_hi + x_base * ldc, cat_lo + x_base * ldc, ldc, 0};
     Planes B{lw.w1_hi, lw.w1_lo, 2 * C, 0};
+    OutMaps om;
+    LB_TRY(fill_out_maps(&om, w.h_hi + x_base * ldc, w.h_lo + x_base * ldc, ldc, nullptr, 0, 2 * C, x_rows, 1));
     typename Epi::Params ep{1, nullptr, 1, nullptr, 0, w.h_hi + x_base * ldc, w.h_lo + x_base * ldc,
-                            static_cast<int>(ldc), 0, lw.s_1};
+                            static_cast<int>(ldc), 0, lw.s_1, om};
     LB_TRY((launch_gemm<BN, Epi>(TAG_MLP1, A, B, 1, static_cast<int>(x_rows), 2 * C, 2 * C, 0, ep, stream)));
   }
   // 6. mlp[2] + norm2 + residual -> cat[:, 0:C] (and x_f32 after the last layer)   [transformer.py:55-58]
@@ -681,10 +753,13 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
     Planes A{w.h_hi + x_base * ldc, w.h_lo + x_base * ldc, ldc, 0};
     Planes B{lw.w2_hi, lw.w2_lo, 2 * C, 0};
     float* xf = write_f32 ? st.x_f32 + x_base * C : nullptr;
+    OutMaps om;
+    LB_TRY(fill_out_maps(&om, static_cast<__half*>(st.cat_hi) + x_base * ldc, static_cast<__half*>(st.cat_lo) + x_base * ldc, ldc, xf,
+                         C, C, x_rows, 1));
     typename Epi::Params ep{lw.ln2_g, lw.ln2_b, 1e-5f, nullptr, 0, cat_hi + x_base * ldc, cat_lo + x_base * ldc,
                             static_cast<int>(ldc), xf, C,
                             static_cast<__half*>(st.cat_hi) + x_base * ldc,
-                            static_cast<__half*>(st.cat_lo) + x_base * ldc, static_cast<int>(ldc), 0, lw.s_2};
+                            static_cast<__half*>(st.cat_lo) + x_base * ldc, static_cast<int>(ldc), 0, lw.s_2, om};
     LB_TRY((launch_gemm<BN, Epi>(TAG_MLP2_LN, A, B, 1, static_cast<int>(x_rows), C, 2 * C, 0, ep, stream)));
   }
   return 0;
@@ -883,16 +958,15 @@ int lb_gemm_split(const void* a_hi, const void* a_lo, long lda, long a_batch_str
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const char* pe = getenv("LOFTR_B200_PROBE_NULL_EPI");   // measurement probe of the main loop (tools/gemm_probe.py)
   const int skip = pe ? atoi(pe) : 0;
-  CUtensorMap tm_out;
-  memset(&tm_out, 0, sizeof(tm_out));
-  if (skip == 3) LB_TRY(make_out_map_f32(&tm_out, out, N, M, batches, ldo));
+  OutMaps om;
+  LB_TRY(fill_out_maps(&om, nullptr, nullptr, 0, out, ldo, N, M, batches));
   if (N % 256 == 0 || N > 128) {
     using Epi = EpiActStore<256>;
-    Epi::Params ep{out, static_cast<int>(ldo), 0, nullptr, 1.f, skip, tm_out};
+    Epi::Params ep{out, static_cast<int>(ldo), 0, nullptr, 1.f, skip, om};
     return launch_gemm<256, Epi>(TAG_GEMM_TEST, A, B, batches, M, N, K, 0, ep, st);
   }
   using Epi = EpiActStore<128>;
-  Epi::Params ep{out, static_cast<int>(ldo), 0, nullptr, 1.f, skip, tm_out};
+  Epi::Params ep{out, static_cast<int>(ldo), 0, nullptr, 1.f, skip, om};
   return launch_gemm<128, Epi>(TAG_GEMM_TEST, A, B, batches, M, N, K, 0, ep, st);
 }
 
@@ -1325,8 +1399,10 @@ int lb_fine_preprocess(const LbFinePreprocessArgs* a, void* ws, size_t ws_bytes,
   using Epi = EpiPlanes<128>;
   Planes A{win_hi, win_lo, a->Cf, 0};
   Planes B{a->merge_w_hi, a->merge_w_lo, a->Cf, 0};
+  OutMaps om;
+  LB_TRY(fill_out_maps(&om, a->cat_hi, a->cat_lo, 2 * a->Cf, a->x_f32, a->Cf, a->Cf, rows, 1));
   Epi::Params ep{0, gbias, WW, a->x_f32, a->Cf, static_cast<__half*>(a->cat_hi), static_cast<__half*>(a->cat_lo),
-                 2 * a->Cf, 0, a->merge_acc_scale};
+                 2 * a->Cf, 0, a->merge_acc_scale, om};
   return launch_gemm<128, Epi>(TAG_FINE_MERGE, A, B, 1, static_cast<int>(rows), a->Cf, a->Cf, 0, ep, st);
 }
 

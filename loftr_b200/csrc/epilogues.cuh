@@ -82,6 +82,20 @@ __device__ __forceinline__ void load_planes32(const __half* hp, const __half* lp
 }
 
 
+// two 32-column groups (e.g. main and correction accumulator) with ONE wait: one exposed TMEM latency instead of two
+__device__ __forceinline__ void load_acc32_pair(uint32_t tmem_acc, int col_a, int col_b, float (&x)[32], float (&y)[32]) {
+  uint32_t v[32], w[32];
+  const uint32_t lane_base = static_cast<uint32_t>(((epi_tid() >> 5) & 3) * 32) << 16;
+  tmem_ld32(tmem_acc + col_a + lane_base, v);
+  tmem_ld32(tmem_acc + col_b + lane_base, w);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    x[j] = __uint_as_float(v[j]);
+    y[j] = __uint_as_float(w[j]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Coalesced epilogue I/O.  An epilogue thread owns one accumulator ROW, so a warp-wide 16-byte store of "my row's
 // next 16 bytes" touches 32 different cache lines (32 sectors per request: the L1 tag stage, not DRAM, becomes the
@@ -92,9 +106,12 @@ __device__ __forceinline__ void load_planes32(const __half* hp, const __half* lp
 #ifndef LB_COALESCE
 #define LB_COALESCE 1
 #endif
-constexpr int kEpiScratchBytes = LB_COALESCE ? 8 * 2048 : 0;   // 8 epilogue warps x 2 KB
+// Per-warp 4 KB staging tile at the START of the epilogue area (1024-byte aligned): a [32 rows x 128 B] fp32 block or
+// two [32 rows x 64 B] plane blocks (hi at +0, lo at +2048) for TMA stores; its first 2 KB double as the transposer
+// scratch of the coalesced load / store helpers below.
+constexpr int kEpiScratchBytes = 8 * 4096;   // 8 epilogue warps x 4 KB
 __device__ __forceinline__ uint32_t* epi_scratch(uint8_t* base) {
-  return reinterpret_cast<uint32_t*>(base + ((epi_tid() >> 5) << 11));
+  return reinterpret_cast<uint32_t*>(base + ((epi_tid() >> 5) << 12));
 }
 template <class T>
 __device__ __forceinline__ T* shfl_ptr(T* p, int src_lane) {
@@ -241,6 +258,73 @@ __device__ __forceinline__ void warp_load_f32x32(uint32_t* scr, const float* ptr
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// TMA-store epilogue path: the warp stages its 32-row block in shared memory in the tensor map's swizzled box layout
+// and ONE lane hands it to the copy engine (cp.async.bulk.tensor ... bulk_group): full-line writes, no per-lane
+// address generation, rows / channels beyond the tensor's extent are clipped by the map (no predicates).  The staging
+// tile is reused only after the engine has read the previous block (wait_group.read).
+struct OutMaps {            // filled on the host (engine.cu make_out_map_*); use == 0 -> the pointer paths are taken
+  CUtensorMap hi, lo, f32;
+  int use;                  // bit 0: planes through TMA, bit 1: fp32 output through TMA
+  int dims;                 // 3: (col, row, batch) coordinates;  4: NHWC (channel, x, y, image) coordinates
+};
+struct OutCoord {           // where this warp's 32-row block goes
+  int c0, c1, c2, c3;       // dims == 3: (col, row0, batch, -);  dims == 4: (channel, x0, y0, image)
+};
+__device__ __forceinline__ void tma_store_box(const CUtensorMap* m, const void* src, int dims, const OutCoord& o) {
+  if (dims == 4) tma_store_4d(m, src, o.c0, o.c1, o.c2, o.c3);
+  else tma_store_3d(m, src, o.c0, o.c1, o.c2);
+}
+// 32 values of my row -> fp16 hi/lo planes, box = 32 columns (64 B, 64-byte swizzle) x 32 rows
+__device__ __forceinline__ void warp_tma_store_planes32(uint32_t* stage, const OutMaps& om, const OutCoord& o, const float (&x)[32]) {
+  const int lane = threadIdx.x & 31;
+  uint32_t h[16], l[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    __half h0, l0, h1, l1;
+    split_f16(x[2 * j], h0, l0);
+    split_f16(x[2 * j + 1], h1, l1);
+    h[j] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
+    l[j] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
+  }
+  if (lane == 0) tma_store_wait_read();
+  __syncwarp();
+  const int sw = (lane >> 1) & 3;   // 64-byte swizzle: 16-byte chunk q of row r lives at q ^ ((r >> 1) & 3)
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    *reinterpret_cast<uint4*>(stage + lane * 16 + ((q ^ sw) << 2)) = make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+    *reinterpret_cast<uint4*>(stage + 512 + lane * 16 + ((q ^ sw) << 2)) = make_uint4(l[4 * q], l[4 * q + 1], l[4 * q + 2], l[4 * q + 3]);
+  }
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_box(&om.hi, stage, om.dims, o);
+    tma_store_box(&om.lo, stage + 512, om.dims, o);
+    tma_store_commit();
+  }
+}
+// 32 fp32 values of my row, box = 32 columns (128 B, 128-byte swizzle) x 32 rows
+__device__ __forceinline__ void warp_tma_store_f32x32(uint32_t* stage, const OutMaps& om, const OutCoord& o, const float (&x)[32]) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) tma_store_wait_read();
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(stage + lane * 32 + ((q ^ (lane & 7)) << 2)) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_box(&om.f32, stage, om.dims, o);
+    tma_store_commit();
+  }
+}
+// The transposer helpers use the first 2 KB of the same tile: wait until the copy engine is done reading it.
+__device__ __forceinline__ void stage_quiesce() {
+  if ((threadIdx.x & 31) == 0) tma_store_wait_read();
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------
 // out[row, col] = act(acc) * rowmask[row];  act = elu(x)+1 for col < elu_cols, identity otherwise.
 // Covers q/k/v projection + feature map + padding mask of LinearAttention
@@ -253,18 +337,14 @@ struct EpiActStore {
     int elu_cols;            // columns [0, elu_cols) get elu+1
     const uint8_t* rowmask;  // optional [batches*M] (1 = valid)
     float acc_scale;         // 2^-e: undoes the power-of-two pre-scaling of the weight planes (exact)
-    int skip;                // probe mode (LOFTR_B200_PROBE_NULL_EPI, lb_gemm_split only): 1 = drain nothing, 2 = TMEM loads only,
-                             // 3 = TMA-store epilogue (tm_out)
-    CUtensorMap tm_out;      // fp32 [batches][M][N], box 32 x 32, 128-byte swizzle (mode 3)
+    int skip;                // probe mode (LOFTR_B200_PROBE_NULL_EPI, lb_gemm_split only): 1 = drain nothing, 2 = TMEM loads only
+    OutMaps om;              // om.use & 2: fp32 output through TMA stores
   };
-  static constexpr int kSmemBytes = 8 * 4096;   // per-warp 32 x 128 B staging tile (TMA store) / 2 KB transposer scratch
+  static constexpr int kSmemBytes = kEpiScratchBytes;
   const Params& p;
   const GemmShape& s;
   uint32_t* scr;
-  uint8_t* stage;
-  __device__ EpiActStore(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_), scr(epi_scratch(smem)) {
-    stage = smem + ((epi_tid() >> 5) << 12);
-  }
+  __device__ EpiActStore(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_), scr(epi_scratch(smem)) {}
   __device__ void item_begin(int, int, int) {}
   __device__ void item_end(int, int, int) {}
   __device__ void prefetch(int, int, int) {}
@@ -297,22 +377,8 @@ struct EpiActStore {
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] *= mk;
-      if (p.skip == 3) {
-        // TMA-store epilogue: stage the warp's 32 x 32 fp32 block (128-byte rows, 16-byte chunk q of row r at
-        // q ^ (r & 7) = the 128B swizzle) and let the copy engine write it; rows past M are clipped by the tensor map
-        const int lane = threadIdx.x & 31;
-        if (lane == 0) tma_store_wait_read();          // the previous block of this warp has left the staging tile
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(stage + lane * 128 + ((q ^ (lane & 7)) << 4)) =
-              make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_3d(&p.tm_out, stage, col, m0 + ((epi_tid() >> 5) & 3) * 32, batch);
-          tma_store_commit();
-        }
+      if (p.om.use & 2) {
+        warp_tma_store_f32x32(scr, p.om, OutCoord{col, m0 + ((epi_tid() >> 5) & 3) * 32, batch, 0}, x);
         continue;
       }
       warp_store_f32x32(scr, row_ok ? p.out + grow * p.ld + col : nullptr, x);
@@ -555,24 +621,16 @@ struct EpiLayerNorm {
     int ld_pl;
     int pl_col0;
     float acc_scale;        // 2^-e of the weight planes
+    OutMaps om;             // TMA-store maps of (out_hi, out_lo) [based at column pl_col0] and out_f32
   };
-  static constexpr int kSmemBytes = kEpiScratchBytes + 2 * BLOCK_N * 4 + 2 * 128 * 8 + 128 * 4;
+  // gamma / beta are read through the read-only cache (2 KB, L1-resident): the shared memory goes to the staging tiles
+  static constexpr int kSmemBytes = kEpiScratchBytes + 2 * 128 * 8 + 128 * 4;
   const Params& p;
   const GemmShape& s;
-  float* sg;
-  float* sb;
-  float* s_red;  // [2 halves][128 rows]
+  float* s_red;  // [2 halves][128 rows] float2 + [128] shift
   uint32_t* scr;
   __device__ EpiLayerNorm(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_), scr(epi_scratch(smem)) {
-    smem += kEpiScratchBytes;
-    sg = reinterpret_cast<float*>(smem);
-    sb = sg + BLOCK_N;
-    s_red = sb + BLOCK_N;
-    for (int i = epi_tid(); i < BLOCK_N; i += kEpiThreads) {
-      sg[i] = p.gamma[i];
-      sb[i] = p.beta[i];
-    }
-    epi_bar_sync();
+    s_red = reinterpret_cast<float*>(smem + kEpiScratchBytes);
   }
   __device__ void item_begin(int, int, int) {}
   __device__ void item_end(int, int, int) {}
@@ -644,8 +702,16 @@ struct EpiLayerNorm {
       float x[32];
       load_acc32(tmem_acc, c * 32, x);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = (x[j] * p.acc_scale - mean) * rstd * sg[c * 32 + j] + sb[c * 32 + j];
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + c * 32) + j4);
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + c * 32) + j4);
+        x[4 * j4] = (x[4 * j4] * p.acc_scale - mean) * rstd * g4.x + b4.x;
+        x[4 * j4 + 1] = (x[4 * j4 + 1] * p.acc_scale - mean) * rstd * g4.y + b4.y;
+        x[4 * j4 + 2] = (x[4 * j4 + 2] * p.acc_scale - mean) * rstd * g4.z + b4.z;
+        x[4 * j4 + 3] = (x[4 * j4 + 3] * p.acc_scale - mean) * rstd * g4.w + b4.w;
+      }
       // warp-cooperative (coalesced) residual loads and stores: every lane takes part, invalid rows pass nullptr
+      if (p.om.use && (p.residual || p.res_hi)) stage_quiesce();
       if (p.residual) {
         float r[32];
         warp_load_f32x32(scr, row_ok ? p.residual + grow * p.ld_res + c * 32 : nullptr, r);
@@ -659,10 +725,18 @@ struct EpiLayerNorm {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] += r[j];
       }
-      if (p.out_f32) warp_store_f32x32(scr, row_ok ? p.out_f32 + grow * p.ld_f32 + c * 32 : nullptr, x);
+      const OutCoord oc{c * 32, m0 + ((epi_tid() >> 5) & 3) * 32, batch, 0};
+      if (p.out_f32) {
+        if (p.om.use & 2) warp_tma_store_f32x32(scr, p.om, oc, x);
+        else warp_store_f32x32(scr, row_ok ? p.out_f32 + grow * p.ld_f32 + c * 32 : nullptr, x);
+      }
       if (p.out_hi) {
-        const long off = grow * p.ld_pl + p.pl_col0 + c * 32;
-        warp_store_planes32(scr, row_ok ? p.out_hi + off : nullptr, row_ok ? p.out_lo + off : nullptr, x);
+        if (p.om.use & 1) {
+          warp_tma_store_planes32(scr, p.om, oc, x);
+        } else {
+          const long off = grow * p.ld_pl + p.pl_col0 + c * 32;
+          warp_store_planes32(scr, row_ok ? p.out_hi + off : nullptr, row_ok ? p.out_lo + off : nullptr, x);
+        }
       }
     }
   }
@@ -686,6 +760,7 @@ struct EpiPlanes {
     int ld_pl;
     int pl_col0;
     float acc_scale;      // 2^-e of the weight planes
+    OutMaps om;           // TMA-store maps of (out_hi, out_lo) [based at column pl_col0] and out_f32
   };
   static constexpr int kSmemBytes = kEpiScratchBytes;
   const Params& p;
@@ -725,10 +800,18 @@ struct EpiPlanes {
           x[4 * j + 3] += t.w;
         }
       }
-      if (p.out_f32) warp_store_f32x32(scr, row_ok ? p.out_f32 + grow * p.ld_f32 + col : nullptr, x);
+      const OutCoord oc{col, m0 + ((epi_tid() >> 5) & 3) * 32, batch, 0};
+      if (p.out_f32) {
+        if (p.om.use & 2) warp_tma_store_f32x32(scr, p.om, oc, x);
+        else warp_store_f32x32(scr, row_ok ? p.out_f32 + grow * p.ld_f32 + col : nullptr, x);
+      }
       if (p.out_hi) {
-        const long off = grow * p.ld_pl + p.pl_col0 + col;
-        warp_store_planes32(scr, row_ok ? p.out_hi + off : nullptr, row_ok ? p.out_lo + off : nullptr, x);
+        if (p.om.use & 1) {
+          warp_tma_store_planes32(scr, p.om, oc, x);
+        } else {
+          const long off = grow * p.ld_pl + p.pl_col0 + col;
+          warp_store_planes32(scr, row_ok ? p.out_hi + off : nullptr, row_ok ? p.out_lo + off : nullptr, x);
+        }
       }
     }
   }
@@ -761,6 +844,7 @@ struct EpiConv {
     float* out_f32;       // optional NHWC fp32 [batches*H*W, f32_ld]
     int f32_ld;
     int H_out, W_out, tiles_w;
+    OutMaps om;           // NHWC TMA-store maps (channel, x, y, image): box 32 channels x 16 x 2 pixels
   };
   static constexpr int kChunks = (BLOCK_N + 31) / 32;        // 32-column groups of the tile (the last may be partial)
   static constexpr int kChunksHalf0 = (kChunks + 1) / 2;     // column half 0 takes the first ones
@@ -849,10 +933,9 @@ struct EpiConv {
       const int col = n0 + c * 32;
       if (col >= s.N) break;
       float v[32];
-      load_acc32(tmem_acc, c * 32, v);
       {  // dual accumulator: add the correction products (hi*lo + lo*hi), see gemm_split.cuh
         float corr[32];
-        load_acc32(tmem_acc + BLOCK_N, c * 32, corr);
+        load_acc32_pair(tmem_acc, c * 32, BLOCK_N + c * 32, v, corr);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += corr[j];
       }
@@ -862,23 +945,28 @@ struct EpiConv {
       if (nvalid == 32) {
         // full 32-channel group: warp-cooperative (coalesced) loads / stores, pixels outside the image pass nullptr
         if (p.res_hi) {
+          if (p.om.use) stage_quiesce();
           float r[32];
           warp_load_planes32(scr, ok ? p.res_hi + pix * p.res_ld + col : nullptr, ok ? p.res_lo + pix * p.res_ld + col : nullptr, r);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += r[j];
         }
         if (p.up_hi) {
-          float a[32], b[32];
-          warp_load_planes32(scr, ok ? p.up_hi + u00 + col : nullptr, ok ? p.up_lo + u00 + col : nullptr, a);
-          warp_load_planes32(scr, ok ? p.up_hi + u01 + col : nullptr, ok ? p.up_lo + u01 + col : nullptr, b);
-          const float wy0 = 1.f - wy1, wx0 = 1.f - wx1;
-          float top[32];
+          // the four bilinear neighbours: plain per-thread loads (two rounds of two neighbours); routing these gathers
+          // through the transposer cost more than it saved (l1_out: 1.82 ms vs 1.31 ms, profiles/r2_*)
+          if (ok) {
+            float a[32], b[32];
+            load_planes32(p.up_hi + u00 + col, p.up_lo + u00 + col, a);
+            load_planes32(p.up_hi + u01 + col, p.up_lo + u01 + col, b);
+            const float wy0 = 1.f - wy1, wx0 = 1.f - wx1;
+            float top[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) top[j] = wx0 * a[j] + wx1 * b[j];
-          warp_load_planes32(scr, ok ? p.up_hi + u10 + col : nullptr, ok ? p.up_lo + u10 + col : nullptr, a);
-          warp_load_planes32(scr, ok ? p.up_hi + u11 + col : nullptr, ok ? p.up_lo + u11 + col : nullptr, b);
+            for (int j = 0; j < 32; ++j) top[j] = wx0 * a[j] + wx1 * b[j];
+            load_planes32(p.up_hi + u10 + col, p.up_lo + u10 + col, a);
+            load_planes32(p.up_hi + u11 + col, p.up_lo + u11 + col, b);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += wy0 * top[j] + wy1 * (wx0 * a[j] + wx1 * b[j]);
+            for (int j = 0; j < 32; ++j) v[j] += wy0 * top[j] + wy1 * (wx0 * a[j] + wx1 * b[j]);
+          }
         }
       } else if (ok) {
         // channel tail (e.g. 196 = 6*32 + 4): scalar path
@@ -901,11 +989,17 @@ struct EpiConv {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.01f * v[j];
       }
+      // the warp's 32 accumulator rows are the 2 x 16 pixel block at (tx*16, ty*8 + 2*quarter); channels / pixels
+      // outside the tensor are clipped by the map, so the TMA path also covers the channel tail and image borders
+      const OutCoord oc{col, tx * kConvTileW, ty * kConvTileH + ((epi_tid() >> 5) & 3) * 2, batch};
+      const bool tma_pl = p.out_hi && (p.om.use & 1), tma_f = p.out_f32 && (p.om.use & 2);
+      if (tma_f) warp_tma_store_f32x32(scr, p.om, oc, v);
+      if (tma_pl) warp_tma_store_planes32(scr, p.om, oc, v);
       if (nvalid == 32) {
-        if (p.out_f32) warp_store_f32x32(scr, ok ? p.out_f32 + pix * p.f32_ld + col : nullptr, v);
-        if (p.out_hi)
+        if (p.out_f32 && !tma_f) warp_store_f32x32(scr, ok ? p.out_f32 + pix * p.f32_ld + col : nullptr, v);
+        if (p.out_hi && !tma_pl)
           warp_store_planes32(scr, ok ? p.out_hi + pix * p.out_ld + col : nullptr, ok ? p.out_lo + pix * p.out_ld + col : nullptr, v);
-      } else if (ok) {
+      } else if (ok && !(tma_pl || tma_f)) {
         for (int j = 0; j < nvalid; ++j) {
           if (p.out_f32) p.out_f32[pix * p.f32_ld + col + j] = v[j];
           if (p.out_hi) {

@@ -89,7 +89,7 @@ struct GemmSmem {
   static constexpr int kStageBytes = 2 * kATile + 2 * kBTile;                // hi + lo of A and B
   static constexpr int kStages = (192 * 1024) / kStageBytes;                 // 2 (96 KB) / 3 (64 KB) / 4 (48 KB)
   static constexpr int kRingBytes = kStages * kStageBytes;
-  static constexpr int kBarBytes = 1024;   // barriers + TMEM slot; keeps the epilogue area 1024-byte aligned (TMA-store staging)
+  static constexpr int kBarBytes = 256;    // barriers + TMEM slot, placed behind the epilogue area
 };
 
 // TMEM layout.  kDual: the two correction products (hi*lo, lo*hi) accumulate into a SECOND accumulator that the
@@ -139,17 +139,21 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   constexpr int kCluster = kMode == 0 ? 1 : 2;
   using S = GemmSmem<BLOCK_N, kPair>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // Dynamic smem base is only guaranteed 16B aligned; the swizzled tiles need 1024B.  The padding is applied as
-  // pointer arithmetic on the __shared__ array (NOT through an integer round trip): the compiler must keep seeing
-  // shared-space pointers, otherwise every epilogue smem access becomes a generic LD/ST (measured: stall_lg, 3x slower).
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // Layout: [TMA ring][epilogue area][mbarriers + TMEM slot].  The swizzled tiles (ring, TMA-store staging) need a
+  // 1024-byte aligned base.  With no static shared memory the dynamic window starts 1024-aligned (checked below: a
+  // misaligned base traps instead of corrupting tiles), so nothing is spent on padding; and the pointers stay plain
+  // offsets of the __shared__ array -- through an integer round trip the compiler loses the address space and every
+  // epilogue smem access becomes a generic LD/ST (measured: stall_lg, 3x slower).
+  uint8_t* smem = smem_raw;
   uint8_t* ring = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kRingBytes);
+  uint8_t* epi_smem = smem + S::kRingBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kRingBytes + Epi::kSmemBytes);
   uint64_t* empty_bar = full_bar + S::kStages;
   uint64_t* tmem_full = empty_bar + S::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint8_t* epi_smem = smem + S::kRingBytes + S::kBarBytes;
+  static_assert(Epi::kSmemBytes % 16 == 0, "epilogue area must keep the barriers aligned");
+  if ((smem_u32(smem_raw) & 1023u) != 0) asm volatile("trap;");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;

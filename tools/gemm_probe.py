@@ -23,7 +23,7 @@ for (m, n, k) in [(76800, 256, 256), (76800, 768, 256), (76800, 512, 512), (7680
     out = torch.empty(m, n, dtype=torch.float32, device=dev)
     res = {}
     outs = {}
-    for mode, name in ((0, "store"), (3, "tma_store"), (2, "tmem_ld_only"), (1, "null")):
+    for mode, name in ((0, "store"), (2, "tmem_ld_only"), (1, "null")):
         os.environ["LOFTR_B200_PROBE_NULL_EPI"] = str(mode)
         ts = []
         for it in range(6):
@@ -37,10 +37,10 @@ for (m, n, k) in [(76800, 256, 256), (76800, 768, 256), (76800, 512, 512), (7680
             if it >= 2:
                 ts.append(e0.elapsed_time(e1))
         res[name] = sum(ts) / len(ts)
-        if mode in (0, 3):
+        if mode == 0:
             outs[mode] = out.clone()
-            out.zero_()
-    same = torch.equal(outs[0], outs[3])
+    ref = (a.double() @ w.double().T)
+    same = f"{float((outs[0].double() - ref).abs().max() / ref.abs().max()):.2e}"
     fl = 2.0 * m * n * k * 3
-    print(f"M={m} N={n} K={k}: " + "  ".join(f"{kk} {v * 1e3:7.1f} us ({fl / v / 1e9:6.0f} TF/s issued)" for kk, v in res.items()) + f"  tma==plain: {same}", flush=True)
+    print(f"M={m} N={n} K={k}: " + "  ".join(f"{kk} {v * 1e3:7.1f} us ({fl / v / 1e9:6.0f} TF/s issued)" for kk, v in res.items()) + f"  rel err vs fp64: {same}  (TMA_STORE={os.environ.get('LOFTR_B200_TMA_STORE', '1')})", flush=True)
 os.environ["LOFTR_B200_PROBE_NULL_EPI"] = "0"
