@@ -1101,11 +1101,39 @@ int lb_backbone_forward(const LbBackboneWeights* w, const float* images, int N, 
   LB_TRY(conv(w->l3[2], B.a3, H8, W8, 1, nullptr, nullptr, 0, 0, &B.t3, nullptr, 0));
   LB_TRY(conv(w->l3[3], B.t3, H8, W8, 1, &B.a3, nullptr, 0, 0, &B.x3, nullptr, 0));
   // FPN                                                                             [resnet_fpn.py:107-116]
+  // The x2 bilinear upsampling of the coarser level is a separate bandwidth kernel into a buffer that is dead at
+  // that point (m2 / m1 are only written two launches later); the lateral 1x1 convolution then adds it as a residual.
+  // LOFTR_B200_FUSED_UPSAMPLE=1 restores the in-epilogue four-neighbour gather.
+  static int fused_up = -1;
+  if (fused_up < 0) {
+    const char* e = getenv("LOFTR_B200_FUSED_UPSAMPLE");
+    fused_up = e ? (atoi(e) != 0 ? 1 : 0) : 0;
+  }
+  auto upsample = [&](const BbBuf& src, int sh, int sw, int C, const BbBuf& dst, int dh, int dw) -> int {
+    if (src.ld != dst.ld) return fail("upsample buffers must share the channel stride");
+    const int groups = src.ld / 8;
+    const long total = static_cast<long>(N) * dh * dw * groups;
+    (void)C;
+    upsample2x_planes_kernel<<<cdiv(total, 256), 256, 0, st>>>(src.hi, src.lo, src.ld, sh, sw, dst.hi, dst.lo, dst.ld, dh, dw,
+                                                              groups, total);
+    LB_LAUNCHED();
+    return 0;
+  };
   LB_TRY(conv(w->l3_out, B.x3, H8, W8, 0, nullptr, nullptr, 0, 0, &B.x3o, feat_c_nhwc, d3));
-  LB_TRY(conv(w->l2_out, B.x2, H4, W4, 0, nullptr, &B.x3o, H8, W8, &B.x2l, nullptr, 0));
+  if (fused_up) {
+    LB_TRY(conv(w->l2_out, B.x2, H4, W4, 0, nullptr, &B.x3o, H8, W8, &B.x2l, nullptr, 0));
+  } else {
+    LB_TRY(upsample(B.x3o, H8, W8, d3, B.m2, H4, W4));
+    LB_TRY(conv(w->l2_out, B.x2, H4, W4, 0, &B.m2, nullptr, 0, 0, &B.x2l, nullptr, 0));
+  }
   LB_TRY(conv(w->l2_out2[0], B.x2l, H4, W4, 2, nullptr, nullptr, 0, 0, &B.m2, nullptr, 0));
   LB_TRY(conv(w->l2_out2[1], B.m2, H4, W4, 0, nullptr, nullptr, 0, 0, &B.x2o, nullptr, 0));
-  LB_TRY(conv(w->l1_out, B.x1, H2, W2, 0, nullptr, &B.x2o, H4, W4, &B.x1l, nullptr, 0));
+  if (fused_up) {
+    LB_TRY(conv(w->l1_out, B.x1, H2, W2, 0, nullptr, &B.x2o, H4, W4, &B.x1l, nullptr, 0));
+  } else {
+    LB_TRY(upsample(B.x2o, H4, W4, d2, B.m1, H2, W2));
+    LB_TRY(conv(w->l1_out, B.x1, H2, W2, 0, &B.m1, nullptr, 0, 0, &B.x1l, nullptr, 0));
+  }
   LB_TRY(conv(w->l1_out2[0], B.x1l, H2, W2, 2, nullptr, nullptr, 0, 0, &B.m1, nullptr, 0));
   LB_TRY(conv(w->l1_out2[1], B.m1, H2, W2, 0, nullptr, nullptr, 0, 0, nullptr, feat_f_nhwc, w->l1_out2[1].cout));
   return 0;
