@@ -1101,13 +1101,14 @@ int lb_backbone_forward(const LbBackboneWeights* w, const float* images, int N, 
   LB_TRY(conv(w->l3[2], B.a3, H8, W8, 1, nullptr, nullptr, 0, 0, &B.t3, nullptr, 0));
   LB_TRY(conv(w->l3[3], B.t3, H8, W8, 1, &B.a3, nullptr, 0, 0, &B.x3, nullptr, 0));
   // FPN                                                                             [resnet_fpn.py:107-116]
-  // The x2 bilinear upsampling of the coarser level is a separate bandwidth kernel into a buffer that is dead at
-  // that point (m2 / m1 are only written two launches later); the lateral 1x1 convolution then adds it as a residual.
-  // LOFTR_B200_FUSED_UPSAMPLE=1 restores the in-epilogue four-neighbour gather.
+  // The x2 bilinear upsampling of the coarser level is gathered inside the lateral 1x1 convolution's epilogue (default).
+  // LOFTR_B200_FUSED_UPSAMPLE=0 runs it as a separate bandwidth kernel into a buffer that is dead at that point
+  // (m2 / m1 are only written two launches later) and adds it through the residual path -- measured slower
+  // (l1_outconv: 487 + 1079 us vs 1244 us fused; profiles/r2f_launches_step_separate_upsample.csv).
   static int fused_up = -1;
   if (fused_up < 0) {
     const char* e = getenv("LOFTR_B200_FUSED_UPSAMPLE");
-    fused_up = e ? (atoi(e) != 0 ? 1 : 0) : 0;
+    fused_up = e ? (atoi(e) != 0 ? 1 : 0) : 1;
   }
   auto upsample = [&](const BbBuf& src, int sh, int sw, int C, const BbBuf& dst, int dh, int dw) -> int {
     if (src.ld != dst.ld) return fail("upsample buffers must share the channel stride");
