@@ -497,7 +497,7 @@ struct TfWs {
   __half* h_hi;     // [R, 2C]
   __half* h_lo;
   float* kv;        // [2*n_groups, H, D*D + D]
-  float* kv_part;   // coarse only: max([2*n_groups, H, splits, per], [2*n_groups, m_tiles, H, per]) (split / tile partials)
+  float* kv_part;   // coarse only: max([2*n_groups, H, splits, per], [2*n_groups, m_tiles, 4, H, per]) (split / tile partials)
 };
 constexpr int kKvSplits = 8;
 
@@ -510,7 +510,7 @@ static void carve_tf(Bump& b, TfWs& w, int C, int H, long R, int n_groups, bool 
   w.h_hi = b.take<__half>(static_cast<size_t>(R) * 2 * C);
   w.h_lo = b.take<__half>(static_cast<size_t>(R) * 2 * C);
   w.kv = b.take<float>(static_cast<size_t>(2) * n_groups * H * (D * D + D));
-  const size_t tiles = static_cast<size_t>((max_group_rows + kBlockM - 1) / kBlockM);
+  const size_t tiles = 4 * static_cast<size_t>((max_group_rows + kBlockM - 1) / kBlockM);   // one partial per row quarter
   const size_t parts = tiles > static_cast<size_t>(kKvSplits) ? tiles : static_cast<size_t>(kKvSplits);
   w.kv_part = coarse ? b.take<float>(static_cast<size_t>(2) * n_groups * H * parts * (D * D + D)) : nullptr;
 }
@@ -650,7 +650,7 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
         typename Epi::Params ep{mask ? mask + s_base : nullptr, lw.s_qkv, w.kv_part, H};
         LB_TRY((launch_gemm<256, Epi>(TAG_KV, A, B, n_groups_s, s_group_rows, 2 * C, C, 0, ep, stream)));
         const long total = static_cast<long>(n_groups_s) * H * per;
-        kv_tile_merge_kernel<<<cdiv(total, 256), 256, 0, stream>>>(w.kv_part, m_tiles_s, H * per, w.kv, total);
+        kv_tile_merge_kernel<<<cdiv(total, 256), 256, 0, stream>>>(w.kv_part, 4 * m_tiles_s, H * per, w.kv, total);
         LB_LAUNCHED();
       }
       {

@@ -29,16 +29,23 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
   lo = __float2half_rn(x - __half2float(hi));
 }
 
+// Two values at once, packed as (a | b << 16): cvt.rn.f16x2.f32 (F2FP.PACK_AB) and HADD2.F32 run on the full-rate
+// ALU, whereas the scalar F2F conversions of split_f16 go through the quarter-rate XU pipe (3 per value: measured as the
+// `mio` / `wait` stalls of every plane-writing epilogue).  Bit-identical to split_f16 (round-to-nearest-even both).
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // Write 32 consecutive values of one row as fp16 hi/lo planes (64 bytes each, 16B-aligned).
 __device__ __forceinline__ void store_planes32(__half* hi_ptr, __half* lo_ptr, const float (&x)[32]) {
   uint32_t h[16], l[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    __half h0, l0, h1, l1;
-    split_f16(x[2 * j], h0, l0);
-    split_f16(x[2 * j + 1], h1, l1);
-    h[j] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
-    l[j] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
+    split_f16x2(x[2 * j], x[2 * j + 1], h[j], l[j]);
   }
   uint4* hp = reinterpret_cast<uint4*>(hi_ptr);
   uint4* lp = reinterpret_cast<uint4*>(lo_ptr);
@@ -180,11 +187,7 @@ __device__ __forceinline__ void warp_store_planes32(uint32_t* scr, __half* hi_pt
   uint32_t h[16], l[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    __half h0, l0, h1, l1;
-    split_f16(x[2 * j], h0, l0);
-    split_f16(x[2 * j + 1], h1, l1);
-    h[j] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
-    l[j] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
+    split_f16x2(x[2 * j], x[2 * j + 1], h[j], l[j]);
   }
   warp_store_rows64(scr, reinterpret_cast<uint8_t*>(hi_ptr), h);
   warp_store_rows64(scr, reinterpret_cast<uint8_t*>(lo_ptr), l);
@@ -282,11 +285,7 @@ __device__ __forceinline__ void warp_tma_store_planes32(uint32_t* stage, const O
   uint32_t h[16], l[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    __half h0, l0, h1, l1;
-    split_f16(x[2 * j], h0, l0);
-    split_f16(x[2 * j + 1], h1, l1);
-    h[j] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
-    l[j] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
+    split_f16x2(x[2 * j], x[2 * j + 1], h[j], l[j]);
   }
   if (lane == 0) tma_store_wait_read();
   __syncwarp();
@@ -397,30 +396,27 @@ struct EpiActStore {
 // 128-row tile contributes
 //     KV[d][v] += sum_r K[r][d] V[r][v],   Ksum[d] += sum_r K[r][d]                          (:43-44)
 // which is evaluated on the CUDA cores from a shared-memory staging of the head's K and V columns (thread = 2 d x 8 v
-// outputs over a quarter of the rows, then a 4-way merge) and written as ONE partial per (group, row tile, head):
-// part[batch][m_tile][head][D*D + D]; kv_tile_merge_kernel sums the row tiles in fixed order (bit-reproducible).
+// outputs over a quarter of the rows) and written as one partial per (group, row tile, row quarter, head):
+// part[batch][m_tile][quarter][head][D*D + D]; kv_tile_merge_kernel sums them in fixed order (bit-reproducible).
 template <int BLOCK_N, int D>
 struct EpiKv {
   static_assert(D == 32 && BLOCK_N == 256, "built for the coarse transformer (d_model 256, 8 heads)");
   struct Params {
     const uint8_t* rowmask;  // optional [batches*M] (1 = valid)
     float acc_scale;
-    float* part;             // [batches][m_tiles][H][D*D + D]
+    float* part;             // [batches][m_tiles][4][H][D*D + D]
     int H;
   };
   static constexpr int kHeads = BLOCK_N / (2 * D);      // heads per n-tile (4)
   static constexpr int kPer = D * D + D;
-  static constexpr int kSmemBytes = 2 * 128 * D * 4;    // K and V staging (aliased by the 4-way merge buffer)
-  static_assert(4 * kPer * 4 <= kSmemBytes, "merge buffer must fit in the staging area");
+  static constexpr int kSmemBytes = 2 * 128 * D * 4;    // K and V staging of one head
   const Params& p;
   const GemmShape& s;
   float* sK;   // [128][D], float4 index q of row r stored at q ^ (r & 7)
   float* sV;
-  float* red;  // [4][kPer] aliasing sK/sV
   __device__ EpiKv(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_) {
     sK = reinterpret_cast<float*>(smem);
     sV = sK + 128 * D;
-    red = sK;
   }
   __device__ void item_begin(int, int, int) {}
   __device__ void item_end(int, int, int) {}
@@ -477,32 +473,22 @@ struct EpiKv {
         ks0 += k2.x;
         ks1 += k2.y;
       }
-      epi_bar_sync();   // everyone is done reading the staging area: it becomes the merge buffer
+      // every row quarter writes its own partial (coalesced: a warp covers 16 d-rows x 128 bytes); the four quarters
+      // and the row tiles are summed in fixed order by kv_tile_merge_kernel -- no shared-memory merge, two barriers
+      // per head instead of four
       {
-        float* rg = red + g * kPer;
+        float* out = p.part + (((static_cast<long>(batch) * s.m_tiles + m0 / kBlockM) * 4 + g) * p.H + head0 + j) * kPer;
         const int da = 2 * d2, db = 2 * d2 + 1;
-        *reinterpret_cast<float4*>(rg + da * D + (((2 * v8) ^ (da & 7)) << 2)) = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
-        *reinterpret_cast<float4*>(rg + da * D + (((2 * v8 + 1) ^ (da & 7)) << 2)) = make_float4(acc0[4], acc0[5], acc0[6], acc0[7]);
-        *reinterpret_cast<float4*>(rg + db * D + (((2 * v8) ^ (db & 7)) << 2)) = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
-        *reinterpret_cast<float4*>(rg + db * D + (((2 * v8 + 1) ^ (db & 7)) << 2)) = make_float4(acc1[4], acc1[5], acc1[6], acc1[7]);
+        *reinterpret_cast<float4*>(out + da * D + 8 * v8) = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
+        *reinterpret_cast<float4*>(out + da * D + 8 * v8 + 4) = make_float4(acc0[4], acc0[5], acc0[6], acc0[7]);
+        *reinterpret_cast<float4*>(out + db * D + 8 * v8) = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
+        *reinterpret_cast<float4*>(out + db * D + 8 * v8 + 4) = make_float4(acc1[4], acc1[5], acc1[6], acc1[7]);
         if (v8 == 0) {
-          rg[D * D + da] = ks0;
-          rg[D * D + db] = ks1;
+          out[D * D + da] = ks0;
+          out[D * D + db] = ks1;
         }
       }
-      epi_bar_sync();
-      {
-        float* out = p.part + ((static_cast<long>(batch) * s.m_tiles + m0 / kBlockM) * p.H + head0 + j) * kPer;
-        for (int e = t; e < kPer; e += kEpiThreads) {
-          int src = e;
-          if (e < D * D) {
-            const int d = e / D, v = e - d * D;
-            src = d * D + ((((v >> 2) ^ (d & 7)) << 2) | (v & 3));
-          }
-          out[e] = (red[src] + red[kPer + src]) + (red[2 * kPer + src] + red[3 * kPer + src]);
-        }
-      }
-      epi_bar_sync();   // the merge buffer is the next head's staging area
+      epi_bar_sync();   // the staging area is rewritten for the next head
     }
   }
 };
@@ -585,11 +571,7 @@ struct EpiAttn {
         uint32_t hw[4], lw[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          __half h0, l0, h1, l1;
-          split_f16(o[2 * j] * z, h0, l0);
-          split_f16(o[2 * j + 1] * z, h1, l1);
-          hw[j] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
-          lw[j] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
+          split_f16x2(o[2 * j] * z, o[2 * j + 1] * z, hw[j], lw[j]);
         }
         if (row_ok) {
           *reinterpret_cast<uint4*>(hp + v8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -858,6 +840,17 @@ struct EpiConv {
   __device__ EpiConv(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_), scr(epi_scratch(smem)) {
     s_scale = reinterpret_cast<float*>(smem + kEpiScratchBytes);
     s_shift = s_scale + kCols;
+    if (s.n_tiles == 1) {   // every layer of the backbone: one n-tile -> the folded BatchNorm is staged once per CTA
+      stage_affine(0);
+      epi_bar_sync();
+    }
+  }
+  __device__ void stage_affine(int n0) {
+    for (int j = epi_tid(); j < kCols; j += kEpiThreads) {
+      const int c = n0 + j;
+      s_scale[j] = c < s.N ? p.scale[c] : 0.f;
+      s_shift[j] = c < s.N ? p.shift[c] : 0.f;
+    }
   }
   __device__ void item_begin(int, int, int) {}
   __device__ void item_end(int, int, int) {}
@@ -895,13 +888,10 @@ struct EpiConv {
     }
   }
   __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
-    const int t = epi_tid();
-    for (int j = t; j < kCols; j += kEpiThreads) {
-      const int c = n0 + j;
-      s_scale[j] = c < s.N ? p.scale[c] : 0.f;
-      s_shift[j] = c < s.N ? p.shift[c] : 0.f;
+    if (s.n_tiles > 1) {
+      stage_affine(n0);
+      epi_bar_sync();
     }
-    epi_bar_sync();
     const int row = epi_row();
     const int mt = m0 / kBlockM;
     const int ty = mt / p.tiles_w, tx = mt - ty * p.tiles_w;
@@ -1011,7 +1001,7 @@ struct EpiConv {
         }
       }
     }
-    epi_bar_sync();  // s_scale / s_shift are rewritten by the next tile
+    if (s.n_tiles > 1) epi_bar_sync();  // s_scale / s_shift are rewritten by the next tile
   }
 };
 

@@ -359,11 +359,7 @@ __global__ void __launch_bounds__(32 * H) attn_apply_kernel(const float* __restr
         uint32_t hw[4], lw[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          __half h0, l0, h1, l1;
-          split_f16(o[2 * j] * z, h0, l0);
-          split_f16(o[2 * j + 1] * z, h1, l1);
-          hw[j] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
-          lw[j] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
+          split_f16x2(o[2 * j] * z, o[2 * j + 1] * z, hw[j], lw[j]);
         }
         *reinterpret_cast<uint4*>(hp + v8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
         *reinterpret_cast<uint4*>(lp + v8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -850,11 +846,7 @@ __global__ void upsample2x_planes_kernel(const __half* __restrict__ src_hi, cons
   for (int k = 0; k < 4; ++k) {
     const float u0 = wy0 * (wx0 * v[0][2 * k] + wx1 * v[1][2 * k]) + wy1 * (wx0 * v[2][2 * k] + wx1 * v[3][2 * k]);
     const float u1 = wy0 * (wx0 * v[0][2 * k + 1] + wx1 * v[1][2 * k + 1]) + wy1 * (wx0 * v[2][2 * k + 1] + wx1 * v[3][2 * k + 1]);
-    __half h0, l0, h1, l1;
-    split_f16(u0, h0, l0);
-    split_f16(u1, h1, l1);
-    oh[k] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
-    ol[k] = static_cast<uint32_t>(__half_as_ushort(l0)) | (static_cast<uint32_t>(__half_as_ushort(l1)) << 16);
+    split_f16x2(u0, u1, oh[k], ol[k]);
   }
   const long d = pix * dst_ld + g * 8;
   *reinterpret_cast<uint4*>(dst_hi + d) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
@@ -965,19 +957,12 @@ __global__ void __launch_bounds__(128) conv_stem7x7_v2_kernel(const float* __res
     uint32_t h0[8], l0[8], h1[8], l1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      __half ha, la, hb, lb2;
       float x = fmaxf(fmaf(a0[2 * j], s_sc[c0 + 2 * j], s_sh[c0 + 2 * j]), 0.f);
       float y = fmaxf(fmaf(a0[2 * j + 1], s_sc[c0 + 2 * j + 1], s_sh[c0 + 2 * j + 1]), 0.f);
-      split_f16(x, ha, la);
-      split_f16(y, hb, lb2);
-      h0[j] = static_cast<uint32_t>(__half_as_ushort(ha)) | (static_cast<uint32_t>(__half_as_ushort(hb)) << 16);
-      l0[j] = static_cast<uint32_t>(__half_as_ushort(la)) | (static_cast<uint32_t>(__half_as_ushort(lb2)) << 16);
+      split_f16x2(x, y, h0[j], l0[j]);
       x = fmaxf(fmaf(a1[2 * j], s_sc[c0 + 2 * j], s_sh[c0 + 2 * j]), 0.f);
       y = fmaxf(fmaf(a1[2 * j + 1], s_sc[c0 + 2 * j + 1], s_sh[c0 + 2 * j + 1]), 0.f);
-      split_f16(x, ha, la);
-      split_f16(y, hb, lb2);
-      h1[j] = static_cast<uint32_t>(__half_as_ushort(ha)) | (static_cast<uint32_t>(__half_as_ushort(hb)) << 16);
-      l1[j] = static_cast<uint32_t>(__half_as_ushort(la)) | (static_cast<uint32_t>(__half_as_ushort(lb2)) << 16);
+      split_f16x2(x, y, h1[j], l1[j]);
     }
     uint4* ph = reinterpret_cast<uint4*>(out_hi + pix * out_ld + c0);
     uint4* pl = reinterpret_cast<uint4*>(out_lo + pix * out_ld + c0);
