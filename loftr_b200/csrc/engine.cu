@@ -17,6 +17,7 @@
 #include "gemm_split.cuh"
 #include "simt_kernels.cuh"
 #include "comm.cuh"
+#include "stem_tc.cuh"
 
 namespace lb {
 
@@ -497,7 +498,7 @@ struct TfWs {
   __half* h_hi;     // [R, 2C]
   __half* h_lo;
   float* kv;        // [2*n_groups, H, D*D + D]
-  float* kv_part;   // coarse only: max([2*n_groups, H, splits, per], [2*n_groups, m_tiles, 4, H, per]) (split / tile partials)
+  float* kv_part;   // coarse only: max([2*n_groups, H, splits, per], [2*n_groups, m_tiles, H, per]) (split / tile partials)
 };
 constexpr int kKvSplits = 8;
 
@@ -510,7 +511,7 @@ static void carve_tf(Bump& b, TfWs& w, int C, int H, long R, int n_groups, bool 
   w.h_hi = b.take<__half>(static_cast<size_t>(R) * 2 * C);
   w.h_lo = b.take<__half>(static_cast<size_t>(R) * 2 * C);
   w.kv = b.take<float>(static_cast<size_t>(2) * n_groups * H * (D * D + D));
-  const size_t tiles = 4 * static_cast<size_t>((max_group_rows + kBlockM - 1) / kBlockM);   // one partial per row quarter
+  const size_t tiles = static_cast<size_t>((max_group_rows + kBlockM - 1) / kBlockM);
   const size_t parts = tiles > static_cast<size_t>(kKvSplits) ? tiles : static_cast<size_t>(kKvSplits);
   w.kv_part = coarse ? b.take<float>(static_cast<size_t>(2) * n_groups * H * parts * (D * D + D)) : nullptr;
 }
@@ -650,7 +651,7 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
         typename Epi::Params ep{mask ? mask + s_base : nullptr, lw.s_qkv, w.kv_part, H};
         LB_TRY((launch_gemm<256, Epi>(TAG_KV, A, B, n_groups_s, s_group_rows, 2 * C, C, 0, ep, stream)));
         const long total = static_cast<long>(n_groups_s) * H * per;
-        kv_tile_merge_kernel<<<cdiv(total, 256), 256, 0, stream>>>(w.kv_part, 4 * m_tiles_s, H * per, w.kv, total);
+        kv_tile_merge_kernel<<<cdiv(total, 256), 256, 0, stream>>>(w.kv_part, m_tiles_s, H * per, w.kv, total);
         LB_LAUNCHED();
       }
       {
@@ -1070,7 +1071,33 @@ int lb_backbone_forward(const LbBackboneWeights* w, const float* images, int N, 
   const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8;
 
   // stem: conv 7x7 s2 + BN + ReLU                                                  [resnet_fpn.py:101]
-  if (use_v2(1)) {
+  // default: tensor-core kernel with software im2col (stem_tc.cuh); LOFTR_B200_STEM_TC=0 keeps the CUDA-core kernels
+  static int stem_tc = -1;
+  if (stem_tc < 0) {
+    const char* e = getenv("LOFTR_B200_STEM_TC");
+    stem_tc = e ? (atoi(e) != 0 ? 1 : 0) : 1;
+  }
+  if (stem_tc) {
+    StemTcParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.img = images; sp.N = N; sp.H = H; sp.W = W;
+    sp.wt = w->stem_wt; sp.scale = w->stem_scale; sp.shift = w->stem_shift;
+    sp.tiles_w = cdiv(W2, kConvTileW); sp.tiles_h = cdiv(H2, kConvTileH);
+    sp.om.dims = 4;
+    LB_TRY(make_out_map_nhwc(&sp.om.hi, B.s0.hi, false, 128, W2, H2, N, B.s0.ld));
+    LB_TRY(make_out_map_nhwc(&sp.om.lo, B.s0.lo, false, 128, W2, H2, N, B.s0.ld));
+    sp.om.use = 1;
+    static bool configured[kMaxDevices] = {false};
+    int dev = 0;
+    LB_CUDA(cudaGetDevice(&dev));
+    if (!configured[dev]) {
+      LB_CUDA(cudaFuncSetAttribute(conv_stem7x7_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes));
+      configured[dev] = true;
+    }
+    const long tiles = static_cast<long>(sp.tiles_w) * sp.tiles_h * N;
+    const int grid = static_cast<int>(tiles < sms ? tiles : sms);
+    conv_stem7x7_tc_kernel<<<grid, kStemThreads, kStemSmemBytes, st>>>(sp);
+  } else if (use_v2(1)) {
     conv_stem7x7_v2_kernel<128><<<dim3(cdiv(W2, 256), H2, N), 128, 0, st>>>(images, H, W, w->stem_wt, w->stem_scale,
                                                                             w->stem_shift, B.s0.hi, B.s0.lo, B.s0.ld);
   } else {
@@ -1155,6 +1182,7 @@ struct CmWs {
   uint8_t* flag;
   float* conf;
   int *ext0, *ext1;
+  int* blk_counts;               // per-block match counts of the ordered compaction
 };
 constexpr int kMaxChunks = 32;
 
@@ -1181,6 +1209,7 @@ static void carve_cm(Bump& b, CmWs& w, int n, int L, int S) {
   w.conf = b.take<float>(nl);
   w.ext0 = b.take<int>(2 * static_cast<size_t>(n));
   w.ext1 = b.take<int>(2 * static_cast<size_t>(n));
+  w.blk_counts = b.take<int>((nl + kCompactBlock - 1) / kCompactBlock + 1);
 }
 
 size_t lb_coarse_match_workspace_bytes(int n_pairs, int L, int S) {
@@ -1371,7 +1400,10 @@ int lb_coarse_match(const LbCoarseMatchArgs* a, void* ws, size_t ws_bytes, void*
   cp.capacity = a->capacity;
   cp.b_ids = a->b_ids; cp.i_ids = a->i_ids; cp.j_ids = a->j_ids;
   cp.mconf = a->mconf; cp.mkpts0 = a->mkpts0_c; cp.mkpts1 = a->mkpts1_c; cp.count = a->count;
-  match_compact_kernel<<<1, 1024, 0, st>>>(cp);
+  const int cblocks = cdiv(nl, kCompactBlock);
+  match_count_kernel<<<cblocks, kCompactBlock, 0, st>>>(w.flag, nl, w.blk_counts);
+  LB_LAUNCHED();
+  match_scatter_kernel<<<cblocks, kCompactBlock, 0, st>>>(cp, w.blk_counts);
   LB_LAUNCHED();
   return 0;
 }

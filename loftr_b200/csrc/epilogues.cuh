@@ -396,27 +396,30 @@ struct EpiActStore {
 // 128-row tile contributes
 //     KV[d][v] += sum_r K[r][d] V[r][v],   Ksum[d] += sum_r K[r][d]                          (:43-44)
 // which is evaluated on the CUDA cores from a shared-memory staging of the head's K and V columns (thread = 2 d x 8 v
-// outputs over a quarter of the rows) and written as one partial per (group, row tile, row quarter, head):
-// part[batch][m_tile][quarter][head][D*D + D]; kv_tile_merge_kernel sums them in fixed order (bit-reproducible).
+// outputs over a quarter of the rows, then a 4-way merge) and written as ONE partial per (group, row tile, head):
+// part[batch][m_tile][head][D*D + D]; kv_tile_merge_kernel sums the row tiles in fixed order (bit-reproducible).
 template <int BLOCK_N, int D>
 struct EpiKv {
   static_assert(D == 32 && BLOCK_N == 256, "built for the coarse transformer (d_model 256, 8 heads)");
   struct Params {
     const uint8_t* rowmask;  // optional [batches*M] (1 = valid)
     float acc_scale;
-    float* part;             // [batches][m_tiles][4][H][D*D + D]
+    float* part;             // [batches][m_tiles][H][D*D + D]
     int H;
   };
   static constexpr int kHeads = BLOCK_N / (2 * D);      // heads per n-tile (4)
   static constexpr int kPer = D * D + D;
-  static constexpr int kSmemBytes = 2 * 128 * D * 4;    // K and V staging of one head
+  static constexpr int kSmemBytes = 2 * 128 * D * 4;    // K and V staging (aliased by the 4-way merge buffer)
+  static_assert(4 * kPer * 4 <= kSmemBytes, "merge buffer must fit in the staging area");
   const Params& p;
   const GemmShape& s;
   float* sK;   // [128][D], float4 index q of row r stored at q ^ (r & 7)
   float* sV;
+  float* red;  // [4][kPer] aliasing sK/sV
   __device__ EpiKv(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_) {
     sK = reinterpret_cast<float*>(smem);
     sV = sK + 128 * D;
+    red = sK;
   }
   __device__ void item_begin(int, int, int) {}
   __device__ void item_end(int, int, int) {}
@@ -473,22 +476,32 @@ struct EpiKv {
         ks0 += k2.x;
         ks1 += k2.y;
       }
-      // every row quarter writes its own partial (coalesced: a warp covers 16 d-rows x 128 bytes); the four quarters
-      // and the row tiles are summed in fixed order by kv_tile_merge_kernel -- no shared-memory merge, two barriers
-      // per head instead of four
+      epi_bar_sync();   // everyone is done reading the staging area: it becomes the merge buffer
       {
-        float* out = p.part + (((static_cast<long>(batch) * s.m_tiles + m0 / kBlockM) * 4 + g) * p.H + head0 + j) * kPer;
+        float* rg = red + g * kPer;
         const int da = 2 * d2, db = 2 * d2 + 1;
-        *reinterpret_cast<float4*>(out + da * D + 8 * v8) = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
-        *reinterpret_cast<float4*>(out + da * D + 8 * v8 + 4) = make_float4(acc0[4], acc0[5], acc0[6], acc0[7]);
-        *reinterpret_cast<float4*>(out + db * D + 8 * v8) = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
-        *reinterpret_cast<float4*>(out + db * D + 8 * v8 + 4) = make_float4(acc1[4], acc1[5], acc1[6], acc1[7]);
+        *reinterpret_cast<float4*>(rg + da * D + (((2 * v8) ^ (da & 7)) << 2)) = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
+        *reinterpret_cast<float4*>(rg + da * D + (((2 * v8 + 1) ^ (da & 7)) << 2)) = make_float4(acc0[4], acc0[5], acc0[6], acc0[7]);
+        *reinterpret_cast<float4*>(rg + db * D + (((2 * v8) ^ (db & 7)) << 2)) = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
+        *reinterpret_cast<float4*>(rg + db * D + (((2 * v8 + 1) ^ (db & 7)) << 2)) = make_float4(acc1[4], acc1[5], acc1[6], acc1[7]);
         if (v8 == 0) {
-          out[D * D + da] = ks0;
-          out[D * D + db] = ks1;
+          rg[D * D + da] = ks0;
+          rg[D * D + db] = ks1;
         }
       }
-      epi_bar_sync();   // the staging area is rewritten for the next head
+      epi_bar_sync();
+      {
+        float* out = p.part + ((static_cast<long>(batch) * s.m_tiles + m0 / kBlockM) * p.H + head0 + j) * kPer;
+        for (int e = t; e < kPer; e += kEpiThreads) {
+          int src = e;
+          if (e < D * D) {
+            const int d = e / D, v = e - d * D;
+            src = d * D + ((((v >> 2) ^ (d & 7)) << 2) | (v & 3));
+          }
+          out[e] = (red[src] + red[kPer + src]) + (red[2 * kPer + src] + red[3 * kPer + src]);
+        }
+      }
+      epi_bar_sync();   // the merge buffer is the next head's staging area
     }
   }
 };

@@ -489,7 +489,7 @@ __global__ void match_flag_kernel(const SelectParams p) {
 }
 
 // Ordered stream compaction (ascending (b, i) like torch.where, coarse_matching.py:194) + coarse
-// keypoints (coarse_matching.py:241-250).  Single block: the list is at most n*L entries.
+// keypoints (coarse_matching.py:241-250).
 struct CompactParams {
   long total;          // n*L
   int L, S, w0c, w1c;
@@ -508,52 +508,74 @@ struct CompactParams {
   float* mkpts1;
   int* count;
 };
-__global__ void __launch_bounds__(1024) match_compact_kernel(const CompactParams p) {
-  __shared__ int s_warp[32];
-  __shared__ int s_base;
-  if (threadIdx.x == 0) s_base = 0;
+// Two launches instead of one single-block sweep (which took 0.115 ms at n*L = 38400): per-block flag counts, then
+// every block derives its exclusive offset from the counts of the blocks before it (<= a few hundred integers) and
+// scatters its rows in order.  The output order is the global row order: ascending (b, i).
+constexpr int kCompactBlock = 256;
+__global__ void __launch_bounds__(kCompactBlock) match_count_kernel(const uint8_t* __restrict__ flag, long total,
+                                                                    int* __restrict__ block_counts) {
+  __shared__ int s_warp[kCompactBlock / 32];
+  const long gi = blockIdx.x * static_cast<long>(kCompactBlock) + threadIdx.x;
+  const int f = (gi < total) ? flag[gi] : 0;
+  const unsigned bal = __ballot_sync(0xffffffffu, f);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = __popc(bal);
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (long start = 0; start < p.total; start += 1024) {
-    const long gi = start + threadIdx.x;
-    const int f = (gi < p.total) ? p.flag[gi] : 0;
-    const unsigned bal = __ballot_sync(0xffffffffu, f);
-    const int wpre = __popc(bal & ((1u << lane) - 1));
-    if (lane == 0) s_warp[warp] = __popc(bal);
-    __syncthreads();
-    int woff = 0, tot = 0;
-    for (int k = 0; k < 32; ++k) {
-      const int c = s_warp[k];
-      if (k < warp) woff += c;
-      tot += c;
-    }
-    const int base = s_base;
-    if (f) {
-      const long pos = static_cast<long>(base) + woff + wpre;
-      if (pos < p.capacity) {
-        const int b = static_cast<int>(gi / p.L);
-        const int i = static_cast<int>(gi - static_cast<long>(b) * p.L);
-        const int j = p.row_arg[gi];
-        p.b_ids[pos] = b;
-        p.i_ids[pos] = i;
-        p.j_ids[pos] = j;
-        p.mconf[pos] = p.conf[gi];
-        float s0x = p.scale, s0y = p.scale, s1x = p.scale, s1y = p.scale;
-        if (p.scale0) {
-          s0x = p.scale * p.scale0[2 * b]; s0y = p.scale * p.scale0[2 * b + 1];
-          s1x = p.scale * p.scale1[2 * b]; s1y = p.scale * p.scale1[2 * b + 1];
-        }
-        p.mkpts0[2 * pos] = static_cast<float>(i % p.w0c) * s0x;
-        p.mkpts0[2 * pos + 1] = static_cast<float>(i / p.w0c) * s0y;
-        p.mkpts1[2 * pos] = static_cast<float>(j % p.w1c) * s1x;
-        p.mkpts1[2 * pos + 1] = static_cast<float>(j / p.w1c) * s1y;
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s_base = base + tot;
-    __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int k = 0; k < kCompactBlock / 32; ++k) t += s_warp[k];
+    block_counts[blockIdx.x] = t;
   }
-  if (threadIdx.x == 0) *p.count = s_base;
+}
+__global__ void __launch_bounds__(kCompactBlock) match_scatter_kernel(const CompactParams p, const int* __restrict__ block_counts) {
+  __shared__ int s_warp[kCompactBlock / 32];
+  __shared__ int s_red[kCompactBlock / 32];
+  __shared__ int s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // exclusive offset of this block = sum of the counts of all earlier blocks
+  int part = 0;
+  for (int k = threadIdx.x; k < static_cast<int>(blockIdx.x); k += kCompactBlock) part += block_counts[k];
+  for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) s_red[warp] = part;
+  const long gi = blockIdx.x * static_cast<long>(kCompactBlock) + threadIdx.x;
+  const int f = (gi < p.total) ? p.flag[gi] : 0;
+  const unsigned bal = __ballot_sync(0xffffffffu, f);
+  const int wpre = __popc(bal & ((1u << lane) - 1));
+  if (lane == 0) s_warp[warp] = __popc(bal);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int b = 0;
+    for (int k = 0; k < kCompactBlock / 32; ++k) b += s_red[k];
+    s_base = b;
+  }
+  __syncthreads();
+  int woff = 0, tot = 0;
+  for (int k = 0; k < kCompactBlock / 32; ++k) {
+    const int c = s_warp[k];
+    if (k < warp) woff += c;
+    tot += c;
+  }
+  if (f) {
+    const long pos = static_cast<long>(s_base) + woff + wpre;
+    if (pos < p.capacity) {
+      const int b = static_cast<int>(gi / p.L);
+      const int i = static_cast<int>(gi - static_cast<long>(b) * p.L);
+      const int j = p.row_arg[gi];
+      p.b_ids[pos] = b;
+      p.i_ids[pos] = i;
+      p.j_ids[pos] = j;
+      p.mconf[pos] = p.conf[gi];
+      float s0x = p.scale, s0y = p.scale, s1x = p.scale, s1y = p.scale;
+      if (p.scale0) {
+        s0x = p.scale * p.scale0[2 * b]; s0y = p.scale * p.scale0[2 * b + 1];
+        s1x = p.scale * p.scale1[2 * b]; s1y = p.scale * p.scale1[2 * b + 1];
+      }
+      p.mkpts0[2 * pos] = static_cast<float>(i % p.w0c) * s0x;
+      p.mkpts0[2 * pos + 1] = static_cast<float>(i / p.w0c) * s0y;
+      p.mkpts1[2 * pos] = static_cast<float>(j % p.w1c) * s1x;
+      p.mkpts1[2 * pos + 1] = static_cast<float>(j / p.w1c) * s1y;
+    }
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *p.count = s_base + tot;
 }
 
 // ------------------------------------------------------------------------------------------------
