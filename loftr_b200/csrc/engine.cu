@@ -226,6 +226,23 @@ static int make_out_map_nhwc(CUtensorMap* m, const void* base, bool f32, int C, 
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (NHWC output) failed with CUresult %d", static_cast<int>(r));
   return 0;
 }
+// FPN upsample source planes [N, H, W, ld] (C valid channels) as unswizzled (box_c, kUpW, kUpH, 1) load boxes: the
+// window EpiConv<., true> stages per output tile; channels / pixels outside the tensor arrive as zeros.
+static int make_up_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, long ld, int box_c) {
+  auto enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0) return fail("upsample source planes not 16-byte aligned");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(ld * 2), static_cast<cuuint64_t>(ld * 2) * W,
+                           static_cast<cuuint64_t>(ld * 2) * W * H};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(kUpW), static_cast<cuuint32_t>(kUpH), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (upsample source) failed with CUresult %d", static_cast<int>(r));
+  return 0;
+}
 // planes (+ optional fp32) of a [batches][rows][cols] output
 static int fill_out_maps(OutMaps* om, const void* hi, const void* lo, long ld_pl, const float* f32, long ld_f32, long cols,
                          long rows, long batches) {
@@ -307,7 +324,7 @@ template <int BN, class Epi, bool kDual, int kMode>
 static int launch_raw(int tag, const GemmMaps& maps, const GemmShape& s, const typename Epi::Params& ep, int sms,
                       cudaStream_t st) {
   constexpr int kCluster = kMode == 0 ? 1 : 2;
-  using S = GemmSmem<BN, kMode == 2>;
+  using S = GemmSmem<BN, kMode == 2, Epi::kSmemBytes>;
   constexpr int smem_bytes = S::kRingBytes + S::kBarBytes + Epi::kSmemBytes;
   static_assert(smem_bytes <= 232448, "shared memory budget exceeded");
   auto kern = gemm_split_kernel<BN, Epi, kDual, kMode>;
@@ -409,10 +426,10 @@ static void conv_layout(int cin, int* cin_blocks, int* rem) {
     *rem = 0;
   }
 }
-template <int BN>
+template <int BN, bool kUp = false>
 static int launch_conv(const Planes& in, const Planes& wgt, const Planes& wgt_rem, const ConvDesc& d,
-                       const typename EpiConv<BN>::Params& ep_in, cudaStream_t st) {
-  using Epi = EpiConv<BN>;
+                       const typename EpiConv<BN, kUp>::Params& ep_in, cudaStream_t st) {
+  using Epi = EpiConv<BN, kUp>;
   int sms = 0;
   LB_TRY(device_check(&sms));
   GemmShape s;
@@ -454,8 +471,12 @@ static int launch_conv(const Planes& in, const Planes& wgt, const Planes& wgt_re
   ep.tiles_w = tiles_w;
   // dual accumulator: EpiConv adds the correction accumulator
   if (mode == 2) return launch_raw<BN, Epi, true, 2>(TAG_CONV, mp, s, ep, sms, st);
-  if (mode == 1) return launch_raw<BN, Epi, true, 1>(TAG_CONV, mp, s, ep, sms, st);
-  return launch_raw<BN, Epi, true, 0>(TAG_CONV, mp, s, ep, sms, st);
+  if constexpr (kUp) {   // the staged window only fits beside the pair mode's (half-B) ring
+    return fail("staged-upsample convolution needs the CTA-pair mode");
+  } else {
+    if (mode == 1) return launch_raw<BN, Epi, true, 1>(TAG_CONV, mp, s, ep, sms, st);
+    return launch_raw<BN, Epi, true, 0>(TAG_CONV, mp, s, ep, sms, st);
+  }
 }
 
 // number of n-chunks that gives every SM a few work items when a CTA must sweep many n tiles
@@ -598,14 +619,32 @@ static int run_conv(const ConvRun& r, int N, cudaStream_t st) {
       om.use |= 2;
     }
   }
-#define LB_CONV_CASE(BN)                                                                                              \
+#define LB_CONV_CASE_UP(BN, UP)                                                                                       \
   {                                                                                                                   \
-    EpiConv<BN>::Params ep{w.scale, w.shift, r.act, r.res ? r.res->hi : nullptr, r.res ? r.res->lo : nullptr,       \
-                           r.res ? r.res->ld : 0, r.up ? r.up->hi : nullptr, r.up ? r.up->lo : nullptr,              \
-                           r.up ? r.up->ld : 0, r.up_h, r.up_w, r.out ? r.out->hi : nullptr,                          \
-                           r.out ? r.out->lo : nullptr, r.out ? r.out->ld : 0, r.out_f32, r.f32_ld, 0, 0, 0, om};     \
-    return launch_conv<BN>(in, wg, wr, d, ep, st);                                                                    \
+    EpiConv<BN, UP>::Params ep{w.scale, w.shift, r.act, r.res ? r.res->hi : nullptr, r.res ? r.res->lo : nullptr,   \
+                               r.res ? r.res->ld : 0, r.up ? r.up->hi : nullptr, r.up ? r.up->lo : nullptr,          \
+                               r.up ? r.up->ld : 0, r.up_h, r.up_w, r.out ? r.out->hi : nullptr,                      \
+                               r.out ? r.out->lo : nullptr, r.out ? r.out->ld : 0, r.out_f32, r.f32_ld, 0, 0, 0, om, \
+                               um};                                                                                   \
+    if (UP) {                                                                                                         \
+      LB_TRY(make_up_map(&ep.um.hi, r.up->hi, d.Cout, r.up_w, r.up_h, N, r.up->ld, EpiConv<BN, UP>::kUpBoxC));        \
+      LB_TRY(make_up_map(&ep.um.lo, r.up->lo, d.Cout, r.up_w, r.up_h, N, r.up->ld, EpiConv<BN, UP>::kUpBoxC));        \
+    }                                                                                                                 \
+    return launch_conv<BN, UP>(in, wg, wr, d, ep, st);                                                                \
   }
+#define LB_CONV_CASE(BN) LB_CONV_CASE_UP(BN, false)
+  UpMaps um;
+  memset(&um, 0, sizeof(um));
+  // FPN laterals: stage the upsample source window in shared memory (exact x2 grids; LOFTR_B200_UP_STAGE=0: the
+  // per-thread global loads of the first generation)
+  static int up_stage = -1;
+  if (up_stage < 0) {
+    const char* e = getenv("LOFTR_B200_UP_STAGE");
+    up_stage = e ? (atoi(e) != 0 ? 1 : 0) : 1;
+  }
+  const bool staged_up = up_stage && r.up && d.H_out == 2 * r.up_h && d.W_out == 2 * r.up_w && w.cout > 128 &&
+                         kernel_mode(TAG_CONV) == 2 &&
+                         ((d.H_out + kConvTileH - 1) / kConvTileH) * ((d.W_out + kConvTileW - 1) / kConvTileW) >= 2;
   // output-channel tile: the smallest built N that covers Cout (196 -> 208: 13 x 16, no MMAs on 60 padding columns)
   static int n208 = -1;   // LOFTR_B200_CONV_N208=0: 256-column tiles for Cout = 196 (first-generation tiling)
   if (n208 < 0) {
@@ -613,9 +652,16 @@ static int run_conv(const ConvRun& r, int N, cudaStream_t st) {
     n208 = e ? (atoi(e) != 0 ? 1 : 0) : 1;
   }
   if (w.cout <= 128) LB_CONV_CASE(128)
-  if (w.cout <= 208 && n208) LB_CONV_CASE(208)
-  if (w.cout <= 256) LB_CONV_CASE(256)
+  if (w.cout <= 208 && n208) {
+    if (staged_up) LB_CONV_CASE_UP(208, true)
+    LB_CONV_CASE(208)
+  }
+  if (w.cout <= 256) {
+    if (staged_up && w.cout > 208) LB_CONV_CASE_UP(256, true)
+    LB_CONV_CASE(256)
+  }
 #undef LB_CONV_CASE
+#undef LB_CONV_CASE_UP
   return fail("convolutions with more than 256 output channels are not built");
 }
 

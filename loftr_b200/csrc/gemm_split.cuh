@@ -82,14 +82,18 @@ __device__ __forceinline__ uint64_t umma_desc_k(uint32_t smem_addr) {
 constexpr uint32_t pow2_at_least(uint32_t x) { return x <= 32 ? 32 : x <= 64 ? 64 : x <= 128 ? 128 : x <= 256 ? 256 : 512; }
 
 // Shared-memory ring.  kPair (cta_group::2): a CTA stages its own 128 rows of A and only its HALF of the B tile.
-template <int BLOCK_N, bool kPair = false>
+// kEpiBytes = the epilogue's own area: an epilogue that stages a lot (EpiConv<., true>) gets a shallower ring.
+template <int BLOCK_N, bool kPair = false, int kEpiBytes = 0>
 struct GemmSmem {
   static constexpr int kATile = kBlockM * kBlockK * 2;                       // 16 KB per plane
   static constexpr int kBTile = (kPair ? BLOCK_N / 2 : BLOCK_N) * kBlockK * 2;  // per plane
   static constexpr int kStageBytes = 2 * kATile + 2 * kBTile;                // hi + lo of A and B
-  static constexpr int kStages = (192 * 1024) / kStageBytes;                 // 2 (96 KB) / 3 (64 KB) / 4 (48 KB)
-  static constexpr int kRingBytes = kStages * kStageBytes;
   static constexpr int kBarBytes = 256;    // barriers + TMEM slot, placed behind the epilogue area
+  static constexpr int kFit = (232448 - kBarBytes - kEpiBytes) / kStageBytes;
+  static constexpr int kWant = (192 * 1024) / kStageBytes;                   // 2 (96 KB) / 3 (64 KB) / 4 (48 KB)
+  static constexpr int kStages = kFit < kWant ? kFit : kWant;
+  static_assert(kStages >= 2, "the TMA ring needs two stages");
+  static constexpr int kRingBytes = kStages * kStageBytes;
 };
 
 // TMEM layout.  kDual: the two correction products (hi*lo, lo*hi) accumulate into a SECOND accumulator that the
@@ -137,7 +141,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   constexpr bool kPair = kMode == 2;
   constexpr bool kMcast = kMode == 1;
   constexpr int kCluster = kMode == 0 ? 1 : 2;
-  using S = GemmSmem<BLOCK_N, kPair>;
+  using S = GemmSmem<BLOCK_N, kPair, Epi::kSmemBytes>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // Layout: [TMA ring][epilogue area][mbarriers + TMEM slot].  The swizzled tiles (ring, TMA-store staging) need a
   // 1024-byte aligned base.  With no static shared memory the dynamic window starts 1024-aligned (checked below: a
