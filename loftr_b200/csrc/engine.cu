@@ -426,10 +426,10 @@ static void conv_layout(int cin, int* cin_blocks, int* rem) {
     *rem = 0;
   }
 }
-template <int BN, bool kUp = false>
+template <int BN, int kUpMode = 0>
 static int launch_conv(const Planes& in, const Planes& wgt, const Planes& wgt_rem, const ConvDesc& d,
-                       const typename EpiConv<BN, kUp>::Params& ep_in, cudaStream_t st) {
-  using Epi = EpiConv<BN, kUp>;
+                       const typename EpiConv<BN, kUpMode>::Params& ep_in, cudaStream_t st) {
+  using Epi = EpiConv<BN, kUpMode>;
   int sms = 0;
   LB_TRY(device_check(&sms));
   GemmShape s;
@@ -471,10 +471,12 @@ static int launch_conv(const Planes& in, const Planes& wgt, const Planes& wgt_re
   ep.tiles_w = tiles_w;
   // dual accumulator: EpiConv adds the correction accumulator
   if (mode == 2) return launch_raw<BN, Epi, true, 2>(TAG_CONV, mp, s, ep, sms, st);
-  if constexpr (kUp) {   // the staged window only fits beside the pair mode's (half-B) ring
+  if constexpr (kUpMode == 1) {   // the staged window only fits beside the pair mode's (half-B) ring
     return fail("staged-upsample convolution needs the CTA-pair mode");
   } else {
-    if (mode == 1) return launch_raw<BN, Epi, true, 1>(TAG_CONV, mp, s, ep, sms, st);
+    if constexpr (kUpMode == 0) {   // the multicast experiment is only built for the plain epilogue
+      if (mode == 1) return launch_raw<BN, Epi, true, 1>(TAG_CONV, mp, s, ep, sms, st);
+    }
     return launch_raw<BN, Epi, true, 0>(TAG_CONV, mp, s, ep, sms, st);
   }
 }
@@ -626,13 +628,17 @@ static int run_conv(const ConvRun& r, int N, cudaStream_t st) {
                                r.up ? r.up->ld : 0, r.up_h, r.up_w, r.out ? r.out->hi : nullptr,                      \
                                r.out ? r.out->lo : nullptr, r.out ? r.out->ld : 0, r.out_f32, r.f32_ld, 0, 0, 0, om, \
                                um};                                                                                   \
-    if (UP) {                                                                                                         \
+    if (UP == 1) {                                                                                                    \
       LB_TRY(make_up_map(&ep.um.hi, r.up->hi, d.Cout, r.up_w, r.up_h, N, r.up->ld, EpiConv<BN, UP>::kUpBoxC));        \
       LB_TRY(make_up_map(&ep.um.lo, r.up->lo, d.Cout, r.up_w, r.up_h, N, r.up->ld, EpiConv<BN, UP>::kUpBoxC));        \
     }                                                                                                                 \
     return launch_conv<BN, UP>(in, wg, wr, d, ep, st);                                                                \
   }
-#define LB_CONV_CASE(BN) LB_CONV_CASE_UP(BN, false)
+#define LB_CONV_CASE(BN)                                                                                              \
+  {                                                                                                                   \
+    if (r.up) LB_CONV_CASE_UP(BN, 2)                                                                                  \
+    LB_CONV_CASE_UP(BN, 0)                                                                                            \
+  }
   UpMaps um;
   memset(&um, 0, sizeof(um));
   // FPN laterals: stage the upsample source window in shared memory (exact x2 grids; LOFTR_B200_UP_STAGE=0: the
@@ -653,11 +659,11 @@ static int run_conv(const ConvRun& r, int N, cudaStream_t st) {
   }
   if (w.cout <= 128) LB_CONV_CASE(128)
   if (w.cout <= 208 && n208) {
-    if (staged_up) LB_CONV_CASE_UP(208, true)
+    if (staged_up) LB_CONV_CASE_UP(208, 1)
     LB_CONV_CASE(208)
   }
   if (w.cout <= 256) {
-    if (staged_up && w.cout > 208) LB_CONV_CASE_UP(256, true)
+    if (staged_up && w.cout > 208) LB_CONV_CASE_UP(256, 1)
     LB_CONV_CASE(256)
   }
 #undef LB_CONV_CASE
@@ -737,6 +743,31 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
       LB_TRY((launch_gemm<BN, Epi>(TAG_PROJ, Ak, Bk, 1, static_cast<int>(s_rows), 2 * C, C, 0, ek, stream)));
     }
   }
+  // 2+3 for the fine windows: one kernel per pass, KV stays in shared memory (LOFTR_B200_WINDOW_ATTN=0: two kernels)
+  static int window_fused = -1;
+  if (window_fused < 0) {
+    const char* e = getenv("LOFTR_B200_WINDOW_ATTN");
+    window_fused = e ? (atoi(e) != 0 ? 1 : 0) : 1;
+  }
+  const bool one_kernel = D == 16 && H == 8 && window_fused && s_group_rows <= 32 && x_group_rows == s_group_rows &&
+                          n_groups_x == n_groups_s;
+  if (one_kernel) {
+    int sms = 0;
+    LB_TRY(device_check(&sms));
+    const int grid = n_groups_x < 3 * sms ? n_groups_x : 3 * sms;   // 3 resident blocks per SM (60 KB, <= 85 registers)
+    const int wa_smem = (H * (D * D + D) + 4 * x_group_rows * C) * static_cast<int>(sizeof(float));
+    static bool wa_configured[kMaxDevices] = {false};
+    int dev = 0;
+    LB_CUDA(cudaGetDevice(&dev));
+    if (!wa_configured[dev]) {
+      LB_CUDA(cudaFuncSetAttribute(window_attn_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (8 * (16 * 16 + 16) + 4 * 32 * 128) * static_cast<int>(sizeof(float))));
+      wa_configured[dev] = true;
+    }
+    window_attn_kernel<16, 8><<<grid, 256, wa_smem, stream>>>(w.qkv, 3 * C, 0, C, 2 * C, x_base, s_base, x_group_rows,
+                                                              n_groups_x, 1e-6f, w.att_hi, w.att_lo, C);
+    LB_LAUNCHED();
+  } else {
   // 2. KV = K^T V and Ksum per (source group, head)            [linear_attention.py:43-44]
   if (D == 32) {
     const int rps = cdiv(cdiv(s_group_rows, kKvSplits), 32) * 32;
@@ -767,6 +798,7 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
                                                                       w.kv, 1e-6f, w.att_hi, w.att_lo, C);
   }
   LB_LAUNCHED();
+  }  // !one_kernel
   }  // !fused
   // 4. merge + norm1 -> cat[:, C:2C]                            [transformer.py:51-52]
   {
@@ -1489,7 +1521,11 @@ int lb_fine_preprocess(const LbFinePreprocessArgs* a, void* ws, size_t ws_bytes,
   g.w0c = a->w0c; g.w1c = a->w1c; g.stride = a->stride; g.W = a->W; g.Cf = a->Cf; g.M = a->M;
   g.b_ids = a->b_ids; g.i_ids = a->i_ids; g.j_ids = a->j_ids;
   g.out_hi = win_hi; g.out_lo = win_lo; g.ld = a->Cf;
-  fine_gather_kernel<<<static_cast<unsigned>(2 * a->M), 256, 0, st>>>(g);
+  const bool vec8 = a->sc0 == 1 && a->sc1 == 1 && a->Cf % 8 == 0 && g.ld % 8 == 0 && a->sw0 % 4 == 0 && a->sw1 % 4 == 0 &&
+                    a->sh0 % 4 == 0 && a->sh1 % 4 == 0 && a->sn0 % 4 == 0 && a->sn1 % 4 == 0 &&
+                    (reinterpret_cast<uintptr_t>(a->feat_f0) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->feat_f1) & 15) == 0;
+  if (vec8) fine_gather_vec8_kernel<<<static_cast<unsigned>(2 * a->M), 256, 0, st>>>(g);
+  else fine_gather_kernel<<<static_cast<unsigned>(2 * a->M), 256, 0, st>>>(g);
   LB_LAUNCHED();
 
   FineBiasParams fb;

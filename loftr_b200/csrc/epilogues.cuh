@@ -822,17 +822,21 @@ struct EpiPlanes {
 //   y = relu / leaky_relu(0.01) / identity
 // written as NHWC fp16 planes (the next convolution's A operand) and / or NHWC fp32.
 //
-// kUp = true (the two FPN lateral 1x1 convolutions): the 6 x 10 source pixels whose bilinear footprints cover the
+// kUpMode selects the FPN merge: 0 = none (every other layer: no upsample code, leanest registers), 1 = staged window,
+// 2 = per-thread global gathers (any shape).
+// kUpMode = 1 (the two FPN lateral 1x1 convolutions): the 6 x 10 source pixels whose bilinear footprints cover the
 // 8 x 16 output tile are fetched ONCE per tile by TMA into shared memory (boxes of 200 / 2 x 136 channels: the pixel
 // stride of 100 / 68 words keeps the quarter-warp LDS.128 conflict-free) while the tile's MMAs run; the four
-// neighbours of a pixel are then shared-memory reads.  With per-thread global loads (kUp = false, any shape) the
+// neighbours of a pixel are then shared-memory reads.  With per-thread global loads (kUpMode = 2) the
 // kernel is bound by L1 tag lookups: 32 LDG.128 per thread and 32-channel group, each touching ~16 lines.
 struct UpMaps {
   CUtensorMap hi, lo;   // upsample source planes [batches, up_h, up_w, C], unswizzled boxes (kUpBoxC, 10, 6, 1)
 };
 constexpr int kUpW = 10, kUpH = 6;
-template <int BLOCK_N, bool kUp = false>
+template <int BLOCK_N, int kUpMode = 0>
 struct EpiConv {
+  static constexpr bool kUp = kUpMode == 1;      // staged window
+  static constexpr bool kUpAny = kUpMode != 0;
   struct Params {
     const float* scale;   // [N]
     const float* shift;   // [N]
@@ -943,7 +947,7 @@ struct EpiConv {
         prefetch_l2(p.res_lo + pix * p.res_ld + c);
       }
     }
-    if (p.up_hi && !kUp) {
+    if (kUpMode == 2 && p.up_hi) {
       const float sh = p.H_out > 1 ? static_cast<float>(p.up_h - 1) / static_cast<float>(p.H_out - 1) : 0.f;
       const float sw = p.W_out > 1 ? static_cast<float>(p.up_w - 1) / static_cast<float>(p.W_out - 1) : 0.f;
       const int y0 = static_cast<int>(sh * y), x0 = static_cast<int>(sw * x);
@@ -974,7 +978,7 @@ struct EpiConv {
     // kUp: u.. are fp16-element offsets of the neighbour pixels inside one staged box, else into the global planes
     long u00 = 0, u01 = 0, u10 = 0, u11 = 0;
     float wy1 = 0.f, wx1 = 0.f;
-    if (p.up_hi && ok) {
+    if (kUpAny && p.up_hi && ok) {
       const float sh = p.H_out > 1 ? static_cast<float>(p.up_h - 1) / static_cast<float>(p.H_out - 1) : 0.f;
       const float sw = p.W_out > 1 ? static_cast<float>(p.up_w - 1) / static_cast<float>(p.W_out - 1) : 0.f;
       const float fy = sh * y, fx = sw * x;
@@ -1003,6 +1007,9 @@ struct EpiConv {
     }
     const int c_begin = epi_half() == 0 ? 0 : kChunksHalf0;
     const int c_end = epi_half() == 0 ? kChunksHalf0 : kChunks;
+    // launch parameters read once per tile (inside the chunk loop each constant-bank load was an exposed latency)
+    const int act = p.act;
+    const bool tma_pl = p.out_hi && (p.om.use & 1), tma_f = p.out_f32 && (p.om.use & 2);
 #pragma unroll 1
     for (int c = c_begin; c < c_end; ++c) {
       const int col = n0 + c * 32;
@@ -1026,7 +1033,7 @@ struct EpiConv {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += r[j];
         }
-        if (p.up_hi) {
+        if (kUpAny && p.up_hi) {
           // the four bilinear neighbours: plain per-thread loads (two rounds of two neighbours); routing these gathers
           // through the transposer cost more than it saved (l1_out: 1.82 ms vs 1.31 ms, profiles/r2_*)
           if (ok) {
@@ -1052,14 +1059,17 @@ struct EpiConv {
           }
         }
       } else if (ok) {
-        // channel tail (e.g. 196 = 6*32 + 4): scalar path
+        // channel tail (e.g. 196 = 6*32 + 4): scalar path.  Fully unrolled with a predicate: a run-time trip count
+        // would index v[] dynamically and push the whole array through local memory (LDL/STL in every chunk)
         const float wy0 = 1.f - wy1, wx0 = 1.f - wx1;
-        for (int j = 0; j < nvalid; ++j) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j >= nvalid) continue;
           if (p.res_hi) {
             const long o = pix * p.res_ld + col + j;
             v[j] += __half2float(p.res_hi[o]) + __half2float(p.res_lo[o]);
           }
-          if (p.up_hi) {
+          if (kUpAny && p.up_hi) {
             const int box = kUpBoxes > 1 ? (c * 32) / 128 : 0;
             const __half* uh = kUp ? reinterpret_cast<const __half*>(s_up + box * kUpBoxBytes) + (c * 32 - box * 128) : p.up_hi + col;
             const __half* ul = kUp ? reinterpret_cast<const __half*>(s_up + kUpPlaneBytes + box * kUpBoxBytes) + (c * 32 - box * 128)
@@ -1069,17 +1079,16 @@ struct EpiConv {
           }
         }
       }
-      if (p.act == 1) {
+      if (act == 1) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-      } else if (p.act == 2) {
+      } else if (act == 2) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.01f * v[j];
       }
       // the warp's 32 accumulator rows are the 2 x 16 pixel block at (tx*16, ty*8 + 2*quarter); channels / pixels
       // outside the tensor are clipped by the map, so the TMA path also covers the channel tail and image borders
       const OutCoord oc{col, tx * kConvTileW, ty * kConvTileH + ((epi_tid() >> 5) & 3) * 2, batch};
-      const bool tma_pl = p.out_hi && (p.om.use & 1), tma_f = p.out_f32 && (p.om.use & 2);
       if (tma_f) warp_tma_store_f32x32(scr, p.om, oc, v);
       if (tma_pl) warp_tma_store_planes32(scr, p.om, oc, v);
       if (nvalid == 32) {
@@ -1087,7 +1096,9 @@ struct EpiConv {
         if (p.out_hi && !tma_pl)
           warp_store_planes32(scr, ok ? p.out_hi + pix * p.out_ld + col : nullptr, ok ? p.out_lo + pix * p.out_ld + col : nullptr, v);
       } else if (ok && !(tma_pl || tma_f)) {
-        for (int j = 0; j < nvalid; ++j) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j >= nvalid) continue;
           if (p.out_f32) p.out_f32[pix * p.f32_ld + col + j] = v[j];
           if (p.out_hi) {
             __half hh, ll;
@@ -1359,7 +1370,9 @@ struct EpiConfStore {
         if (col + 32 <= s.N && (s.N & 3) == 0) {
           store_f32x32(orow + col, z);
         } else {
-          for (int j = 0; j < 32 && col + j < s.N; ++j) orow[col + j] = z[j];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col + j < s.N) orow[col + j] = z[j];   // predicated, not a run-time trip count: z[] stays in registers
         }
       }
     }

@@ -369,6 +369,138 @@ __global__ void __launch_bounds__(32 * H) attn_apply_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fine (window) linear attention in ONE kernel: kv_window_kernel + attn_apply_kernel<16, 8> back to back per window
+// (reference linear_attention.py:43-46 on the [M, 25, 128] window sequences of fine_preprocess.py).  One block takes
+// windows g, g + gridDim.x, ...; KV[h] = K_h^T V_h and Ksum_h are built in shared memory (never in HBM) and warp h /
+// lane r applies them to query row r.  The kernel is latency-bound on the q/k/v reads (ncu: 34 % of the samples wait
+// on them), so the NEXT window's K / V rows travel global -> shared with cp.async into the other half of a double
+// buffer and its query row into registers while the current window is computed.  Same summation order as the
+// two-kernel path: bit-identical output.  Dynamic shared memory: 2 x 2 x rows x 512 B + 8.7 KB (60 KB for 25 rows).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int D, int H>
+__global__ void __launch_bounds__(32 * H, 3) window_attn_kernel(const float* __restrict__ qkv, int ld, int q_col0, int k_col0,
+                                                                int v_col0, long x_row_base, long s_row_base,
+                                                                int rows_per_group, int n_groups, float eps,
+                                                                __half* __restrict__ att_hi, __half* __restrict__ att_lo,
+                                                                int ld_att) {
+  static_assert(D == 16 && H == 8, "fine head layout");
+  constexpr int C = D * H;  // 128
+  constexpr int PER = D * D + D;
+  extern __shared__ __align__(16) float wa_smem[];
+  float* sKV = wa_smem;                                   // [H][PER]
+  float* sKVbuf = wa_smem + H * PER;                      // [2][K | V][rows][C]
+  const int buf_floats = 2 * rows_per_group * C;
+  const int tid = threadIdx.x;
+  const int hd = tid >> 5, lane = tid & 31;
+  const bool has_row = lane < rows_per_group;
+
+  auto issue = [&](int g, int b) {   // K / V rows of window g -> buffer b
+    float* dK = sKVbuf + b * buf_floats;
+    float* dV = dK + rows_per_group * C;
+    for (int i = tid; i < rows_per_group * (C / 4); i += 32 * H) {
+      const int r = i / (C / 4), c4 = (i % (C / 4)) * 4;
+      const float* rowp = qkv + (s_row_base + static_cast<long>(g) * rows_per_group + r) * ld;
+      cp_async16(dK + r * C + c4, rowp + k_col0 + c4);
+      cp_async16(dV + r * C + c4, rowp + v_col0 + c4);
+    }
+  };
+  auto load_q = [&](int g, float (&q)[D]) {
+    const float4* qp = reinterpret_cast<const float4*>(
+        qkv + (x_row_base + static_cast<long>(g) * rows_per_group + lane) * ld + q_col0 + hd * D);
+#pragma unroll
+    for (int j = 0; j < D / 4; ++j) {
+      const float4 t = qp[j];
+      q[4 * j] = t.x; q[4 * j + 1] = t.y; q[4 * j + 2] = t.z; q[4 * j + 3] = t.w;
+    }
+  };
+
+  float q[D], qn[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) q[j] = qn[j] = 0.f;
+  int g = blockIdx.x;
+  if (g < n_groups) {
+    issue(g, 0);
+    if (has_row) load_q(g, q);
+  }
+  cp_async_commit();
+  int b = 0;
+  for (; g < n_groups; g += gridDim.x, b ^= 1) {
+    const int gn = g + gridDim.x;
+    if (gn < n_groups) {
+      issue(gn, b ^ 1);
+      if (has_row) load_q(gn, qn);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();      // this thread's copies of window g have landed ...
+    __syncthreads();         // ... and everybody else's
+    const float* sK = sKVbuf + b * buf_floats;
+    const float* sV = sK + rows_per_group * C;
+    // KV[hd][d][v0..v0+7] and Ksum[hd][d] over the window's rows
+    {
+      const int d = lane >> 1, v0 = (lane & 1) * 8;
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      float ks = 0.f;
+      for (int r = 0; r < rows_per_group; ++r) {
+        const float k = sK[r * C + hd * D + d];
+        const float4 a = *reinterpret_cast<const float4*>(&sV[r * C + hd * D + v0]);
+        const float4 c = *reinterpret_cast<const float4*>(&sV[r * C + hd * D + v0 + 4]);
+        acc[0] = fmaf(k, a.x, acc[0]); acc[1] = fmaf(k, a.y, acc[1]); acc[2] = fmaf(k, a.z, acc[2]); acc[3] = fmaf(k, a.w, acc[3]);
+        acc[4] = fmaf(k, c.x, acc[4]); acc[5] = fmaf(k, c.y, acc[5]); acc[6] = fmaf(k, c.z, acc[6]); acc[7] = fmaf(k, c.w, acc[7]);
+        ks += k;
+      }
+      float* out = sKV + hd * PER + d * D + v0;
+      *reinterpret_cast<float4*>(out) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(out + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      if ((lane & 1) == 0) sKV[hd * PER + D * D + d] = ks;
+    }
+    __syncwarp();   // KV of head hd is produced and consumed by warp hd only
+    // message row = (q . KV) / (q . Ksum + eps) -> fp16 planes
+    if (has_row) {
+      const float* kvh = sKV + hd * PER;
+      const long xrow = x_row_base + static_cast<long>(g) * rows_per_group + lane;
+      float zden = eps;
+#pragma unroll
+      for (int d = 0; d < D; ++d) zden = fmaf(q[d], kvh[D * D + d], zden);
+      const float z = 1.f / zden;
+      __half* hp = att_hi + xrow * ld_att + hd * D;
+      __half* lp = att_lo + xrow * ld_att + hd * D;
+#pragma unroll
+      for (int v8 = 0; v8 < D; v8 += 8) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float4 a = *reinterpret_cast<const float4*>(&kvh[d * D + v8]);
+          const float4 c = *reinterpret_cast<const float4*>(&kvh[d * D + v8 + 4]);
+          o[0] = fmaf(q[d], a.x, o[0]); o[1] = fmaf(q[d], a.y, o[1]);
+          o[2] = fmaf(q[d], a.z, o[2]); o[3] = fmaf(q[d], a.w, o[3]);
+          o[4] = fmaf(q[d], c.x, o[4]); o[5] = fmaf(q[d], c.y, o[5]);
+          o[6] = fmaf(q[d], c.z, o[6]); o[7] = fmaf(q[d], c.w, o[7]);
+        }
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split_f16x2(o[2 * j] * z, o[2 * j + 1] * z, hw[j], lw[j]);
+        *reinterpret_cast<uint4*>(hp + v8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(lp + v8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < D; ++j) q[j] = qn[j];
+    __syncthreads();   // buffer b is refilled by the next iteration's copies
+  }
+  cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Merge log-sum-exp partials: out[i] = base - LSE(parts[:, i] U {dustbin term}).
 //   dual-softmax:  base = 0, no dustbin   -> out = -LSE (the additive log-normaliser)
 //   Sinkhorn:      base = log_mu / log_nu, dustbin term = bin + bin_pot[pair]   (superglue.py:146-147)
@@ -686,6 +818,43 @@ __global__ void fine_gather_kernel(const FineGatherParams p) {
     const long row = win * WW + k;
     p.out_hi[row * p.ld + c] = hh;
     p.out_lo[row * p.ld + c] = ll;
+  }
+}
+
+// Channel-contiguous (NHWC, sc == 1) maps with Cf % 8 == 0: one thread moves 8 channels of one window position --
+// two 16-byte loads, packed split, one 16-byte store per plane (the element-wise kernel above issues 2-byte stores).
+__global__ void __launch_bounds__(256) fine_gather_vec8_kernel(const FineGatherParams p) {
+  const int WW = p.W * p.W;
+  const int c8n = p.Cf >> 3;
+  const long win = blockIdx.x;             // 0 .. 2M-1
+  const int side = win >= p.M ? 1 : 0;
+  const long m = side ? win - p.M : win;
+  const int b = static_cast<int>(p.b_ids[m]);
+  const int idx = static_cast<int>(side ? p.j_ids[m] : p.i_ids[m]);
+  const int wc = side ? p.w1c : p.w0c;
+  const int cy = idx / wc, cx = idx - cy * wc;
+  const float* feat = side ? p.feat1 : p.feat0;
+  const long sn = side ? p.sn1 : p.sn0, sh = side ? p.sh1 : p.sh0, sw = side ? p.sw1 : p.sw0;
+  const int Hf = side ? p.Hf1 : p.Hf0, Wf = side ? p.Wf1 : p.Wf0;
+  for (int e = threadIdx.x; e < WW * c8n; e += blockDim.x) {
+    const int k = e / c8n, c = (e - k * c8n) << 3;
+    const int ky = k / p.W, kx = k - ky * p.W;
+    const int y = p.stride * cy - p.W / 2 + ky;
+    const int x = p.stride * cx - p.W / 2 + kx;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (y >= 0 && y < Hf && x >= 0 && x < Wf) {
+      const float4* src = reinterpret_cast<const float4*>(feat + b * sn + y * sh + x * sw + c);
+      v0 = src[0];
+      v1 = src[1];
+    }
+    uint32_t h[4], l[4];
+    split_f16x2(v0.x, v0.y, h[0], l[0]);
+    split_f16x2(v0.z, v0.w, h[1], l[1]);
+    split_f16x2(v1.x, v1.y, h[2], l[2]);
+    split_f16x2(v1.z, v1.w, h[3], l[3]);
+    const long o = (win * WW + k) * p.ld + c;
+    *reinterpret_cast<uint4*>(p.out_hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(p.out_lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
 
