@@ -426,10 +426,10 @@ static void conv_layout(int cin, int* cin_blocks, int* rem) {
     *rem = 0;
   }
 }
-template <int BN, int kUpMode = 0>
+template <int BN, int kUpMode = 0, bool kDualAcc = true>
 static int launch_conv(const Planes& in, const Planes& wgt, const Planes& wgt_rem, const ConvDesc& d,
-                       const typename EpiConv<BN, kUpMode>::Params& ep_in, cudaStream_t st) {
-  using Epi = EpiConv<BN, kUpMode>;
+                       const typename EpiConv<BN, kUpMode, kDualAcc>::Params& ep_in, cudaStream_t st) {
+  using Epi = EpiConv<BN, kUpMode, kDualAcc>;
   int sms = 0;
   LB_TRY(device_check(&sms));
   GemmShape s;
@@ -469,15 +469,15 @@ static int launch_conv(const Planes& in, const Planes& wgt, const Planes& wgt_re
   ep.H_out = d.H_out;
   ep.W_out = d.W_out;
   ep.tiles_w = tiles_w;
-  // dual accumulator: EpiConv adds the correction accumulator
-  if (mode == 2) return launch_raw<BN, Epi, true, 2>(TAG_CONV, mp, s, ep, sms, st);
+  // dual accumulator (3x3 layers): EpiConv adds the correction accumulator; single accumulator for the short-K 1x1 layers
+  if (mode == 2) return launch_raw<BN, Epi, kDualAcc, 2>(TAG_CONV, mp, s, ep, sms, st);
   if constexpr (kUpMode == 1) {   // the staged window only fits beside the pair mode's (half-B) ring
     return fail("staged-upsample convolution needs the CTA-pair mode");
   } else {
-    if constexpr (kUpMode == 0) {   // the multicast experiment is only built for the plain epilogue
+    if constexpr (kUpMode == 0 && kDualAcc) {   // the multicast experiment is only built for the plain epilogue
       if (mode == 1) return launch_raw<BN, Epi, true, 1>(TAG_CONV, mp, s, ep, sms, st);
     }
-    return launch_raw<BN, Epi, true, 0>(TAG_CONV, mp, s, ep, sms, st);
+    return launch_raw<BN, Epi, kDualAcc, 0>(TAG_CONV, mp, s, ep, sms, st);
   }
 }
 
@@ -621,18 +621,19 @@ static int run_conv(const ConvRun& r, int N, cudaStream_t st) {
       om.use |= 2;
     }
   }
-#define LB_CONV_CASE_UP(BN, UP)                                                                                       \
+#define LB_CONV_CASE_UP(BN, UP) LB_CONV_CASE_ACC(BN, UP, true)
+#define LB_CONV_CASE_ACC(BN, UP, DUAL)                                                                                \
   {                                                                                                                   \
-    EpiConv<BN, UP>::Params ep{w.scale, w.shift, r.act, r.res ? r.res->hi : nullptr, r.res ? r.res->lo : nullptr,   \
+    EpiConv<BN, UP, DUAL>::Params ep{w.scale, w.shift, r.act, r.res ? r.res->hi : nullptr, r.res ? r.res->lo : nullptr,   \
                                r.res ? r.res->ld : 0, r.up ? r.up->hi : nullptr, r.up ? r.up->lo : nullptr,          \
                                r.up ? r.up->ld : 0, r.up_h, r.up_w, r.out ? r.out->hi : nullptr,                      \
                                r.out ? r.out->lo : nullptr, r.out ? r.out->ld : 0, r.out_f32, r.f32_ld, 0, 0, 0, om, \
                                um};                                                                                   \
     if (UP == 1) {                                                                                                    \
-      LB_TRY(make_up_map(&ep.um.hi, r.up->hi, d.Cout, r.up_w, r.up_h, N, r.up->ld, EpiConv<BN, UP>::kUpBoxC));        \
-      LB_TRY(make_up_map(&ep.um.lo, r.up->lo, d.Cout, r.up_w, r.up_h, N, r.up->ld, EpiConv<BN, UP>::kUpBoxC));        \
+      LB_TRY(make_up_map(&ep.um.hi, r.up->hi, d.Cout, r.up_w, r.up_h, N, r.up->ld, EpiConv<BN, UP, DUAL>::kUpBoxC));  \
+      LB_TRY(make_up_map(&ep.um.lo, r.up->lo, d.Cout, r.up_w, r.up_h, N, r.up->ld, EpiConv<BN, UP, DUAL>::kUpBoxC));  \
     }                                                                                                                 \
-    return launch_conv<BN, UP>(in, wg, wr, d, ep, st);                                                                \
+    return launch_conv<BN, UP, DUAL>(in, wg, wr, d, ep, st);                                                          \
   }
 #define LB_CONV_CASE(BN)                                                                                              \
   {                                                                                                                   \
@@ -657,17 +658,29 @@ static int run_conv(const ConvRun& r, int N, cudaStream_t st) {
     const char* e = getenv("LOFTR_B200_CONV_N208");
     n208 = e ? (atoi(e) != 0 ? 1 : 0) : 1;
   }
+  // 1x1 layers (K = Cin <= 256): single accumulator, two TMEM stages (LOFTR_B200_CONV1X1_DUAL=1: the dual layout)
+  static int dual1x1 = -1;
+  if (dual1x1 < 0) {
+    const char* e = getenv("LOFTR_B200_CONV1X1_DUAL");
+    dual1x1 = e ? (atoi(e) != 0 ? 1 : 0) : 0;
+  }
+  const bool single_acc = w.ksize == 1 && !dual1x1 && w.cout > 128 && (staged_up || !r.up);
   if (w.cout <= 128) LB_CONV_CASE(128)
   if (w.cout <= 208 && n208) {
+    if (staged_up && single_acc) LB_CONV_CASE_ACC(208, 1, false)
     if (staged_up) LB_CONV_CASE_UP(208, 1)
+    if (single_acc) LB_CONV_CASE_ACC(208, 0, false)
     LB_CONV_CASE(208)
   }
   if (w.cout <= 256) {
+    if (staged_up && w.cout > 208 && single_acc) LB_CONV_CASE_ACC(256, 1, false)
     if (staged_up && w.cout > 208) LB_CONV_CASE_UP(256, 1)
+    if (single_acc) LB_CONV_CASE_ACC(256, 0, false)
     LB_CONV_CASE(256)
   }
 #undef LB_CONV_CASE
 #undef LB_CONV_CASE_UP
+#undef LB_CONV_CASE_ACC
   return fail("convolutions with more than 256 output channels are not built");
 }
 

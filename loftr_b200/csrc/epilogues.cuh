@@ -202,6 +202,54 @@ __device__ __forceinline__ void warp_store_f32x32(uint32_t* scr, float* ptr, con
   warp_store_rows64(scr, reinterpret_cast<uint8_t*>(ptr), a);
   warp_store_rows64(scr, ptr ? reinterpret_cast<uint8_t*>(ptr) + 64 : nullptr, b);
 }
+// Split form of warp_load_planes32 (coalesced build only): `issue` puts the lane's eight 16-byte global loads in flight
+// (rows lane/4 + 8i, 16-byte group lane%4), `finish` transposes them through the scratch into this lane's row.  An
+// epilogue can issue before it waits for / converts its accumulator group and finish afterwards.
+__device__ __forceinline__ void warp_issue_planes32(const __half* hi_ptr, const __half* lo_ptr, uint4 (&vh)[4], uint4 (&vl)[4]) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane >> 2) + 8 * i;
+    const uint8_t* sh = shfl_ptr(reinterpret_cast<const uint8_t*>(hi_ptr), r);
+    const uint8_t* sl = shfl_ptr(reinterpret_cast<const uint8_t*>(lo_ptr), r);
+    vh[i] = make_uint4(0u, 0u, 0u, 0u);
+    vl[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (sh) vh[i] = *reinterpret_cast<const uint4*>(sh + g * 16);
+    if (sl) vl[i] = *reinterpret_cast<const uint4*>(sl + g * 16);
+  }
+}
+__device__ __forceinline__ void warp_finish_planes32(uint32_t* scr, const uint4 (&vh)[4], const uint4 (&vl)[4], float (&x)[32]) {
+  uint32_t h[16], l[16];
+  const int lane = threadIdx.x & 31;
+  const int g = lane & 3;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = (lane >> 2) + 8 * i;
+      *reinterpret_cast<uint4*>(scr + r * 16 + ((g ^ ((r >> 1) & 3)) << 2)) = pass == 0 ? vh[i] : vl[i];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 v = *reinterpret_cast<const uint4*>(scr + lane * 16 + ((q ^ ((lane >> 1) & 3)) << 2));
+      if (pass == 0) {
+        h[4 * q] = v.x; h[4 * q + 1] = v.y; h[4 * q + 2] = v.z; h[4 * q + 3] = v.w;
+      } else {
+        l[4 * q] = v.x; l[4 * q + 1] = v.y; l[4 * q + 2] = v.z; l[4 * q + 3] = v.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+    const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&l[j]));
+    x[2 * j] = fh.x + fl.x;
+    x[2 * j + 1] = fh.y + fl.y;
+  }
+}
 __device__ __forceinline__ void warp_load_planes32(uint32_t* scr, const __half* hi_ptr, const __half* lo_ptr, float (&x)[32]) {
   uint32_t h[16], l[16];
 #if LB_COALESCE
@@ -833,7 +881,10 @@ struct UpMaps {
   CUtensorMap hi, lo;   // upsample source planes [batches, up_h, up_w, C], unswizzled boxes (kUpBoxC, 10, 6, 1)
 };
 constexpr int kUpW = 10, kUpH = 6;
-template <int BLOCK_N, int kUpMode = 0>
+// kDualAcc mirrors the kernel's kDual: the 3x3 layers (K up to 2304) keep the correction products in a second
+// accumulator; the 1x1 layers (K <= 256: at most 48 MMAs per output) use one accumulator, which halves their TMEM
+// reads and leaves room for two TMEM stages at N = 208 / 256 (their epilogue then overlaps the next tile's MMAs).
+template <int BLOCK_N, int kUpMode = 0, bool kDualAcc = true>
 struct EpiConv {
   static constexpr bool kUp = kUpMode == 1;      // staged window
   static constexpr bool kUpAny = kUpMode != 0;
@@ -865,7 +916,11 @@ struct EpiConv {
   static constexpr int kUpBoxBytes = (kUpBoxData + 127) & ~127;         // its (128-byte aligned) slot
   static constexpr int kUpPlaneBytes = kUpBoxes * kUpBoxBytes;
   static constexpr int kUpOffset = kEpiScratchBytes + 2 * kCols * 4;
-  static constexpr int kSmemBytes = kUpOffset + (kUp ? 2 * kUpPlaneBytes + 16 : 0);
+  // N = 208 has 17.9 KB of shared memory to spare beside its three-stage ring: the residual transposer gets its own
+  // 2 KB per warp there instead of aliasing the TMA-store staging tile, so a chunk's residual read no longer waits for
+  // the copy engine to finish reading the previous chunk's store (11 us per tile in the layer2 conv2 kernels)
+  static constexpr bool kOwnXpose = BLOCK_N == 208 && kUpMode == 0;
+  static constexpr int kSmemBytes = kUpOffset + (kUp ? 2 * kUpPlaneBytes + 16 : 0) + (kOwnXpose ? 8 * 2048 : 0);
   static_assert(kUpOffset % 128 == 0 && kUpBoxBytes % 128 == 0, "TMA destinations are 128-byte aligned");
   static_assert(!kUp || BLOCK_N > 128, "the staged upsample is built for the 196- and 256-channel laterals");
   const Params& p;
@@ -873,6 +928,7 @@ struct EpiConv {
   float* s_scale;
   float* s_shift;
   uint32_t* scr;
+  uint32_t* xscr;       // transposer scratch of the residual loads (== scr unless kOwnXpose)
   uint8_t* s_up;        // [hi | lo][box][6][10][kUpBoxC] fp16
   uint64_t* up_bar;
   uint32_t up_phase = 0;
@@ -880,6 +936,7 @@ struct EpiConv {
     s_scale = reinterpret_cast<float*>(smem + kEpiScratchBytes);
     s_shift = s_scale + kCols;
     s_up = smem + kUpOffset;
+    xscr = kOwnXpose ? reinterpret_cast<uint32_t*>(smem + kUpOffset + ((epi_tid() >> 5) << 11)) : scr;
     up_bar = reinterpret_cast<uint64_t*>(smem + kUpOffset + 2 * kUpPlaneBytes);
     if (kUp) {
       if ((smem_u32(s_up) & 127u) != 0) asm volatile("trap;");
@@ -1014,22 +1071,35 @@ struct EpiConv {
     for (int c = c_begin; c < c_end; ++c) {
       const int col = n0 + c * 32;
       if (col >= s.N) break;
+      const int nvalid = min(32, s.N - col);   // warp-uniform
+#if LB_COALESCE
+      // residual rows of this 32-channel group: requested before the accumulator is fetched and converted
+      const bool res_early = p.res_hi != nullptr && nvalid == 32;
+      uint4 rh[4], rl[4];
+      if (res_early)
+        warp_issue_planes32(ok ? p.res_hi + pix * p.res_ld + col : nullptr, ok ? p.res_lo + pix * p.res_ld + col : nullptr, rh, rl);
+#endif
       float v[32];
-      {  // dual accumulator: add the correction products (hi*lo + lo*hi), see gemm_split.cuh
+      if constexpr (kDualAcc) {  // dual accumulator: add the correction products (hi*lo + lo*hi), see gemm_split.cuh
         float corr[32];
         load_acc32_pair(tmem_acc, c * 32, BLOCK_N + c * 32, v, corr);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += corr[j];
+      } else {
+        load_acc32(tmem_acc, c * 32, v);
       }
-      const int nvalid = min(32, s.N - col);   // warp-uniform
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], s_scale[c * 32 + j], s_shift[c * 32 + j]);
       if (nvalid == 32) {
         // full 32-channel group: warp-cooperative (coalesced) loads / stores, pixels outside the image pass nullptr
         if (p.res_hi) {
-          if (p.om.use) stage_quiesce();
+          if (p.om.use && !kOwnXpose) stage_quiesce();
           float r[32];
-          warp_load_planes32(scr, ok ? p.res_hi + pix * p.res_ld + col : nullptr, ok ? p.res_lo + pix * p.res_ld + col : nullptr, r);
+#if LB_COALESCE
+          warp_finish_planes32(xscr, rh, rl, r);
+#else
+          warp_load_planes32(xscr, ok ? p.res_hi + pix * p.res_ld + col : nullptr, ok ? p.res_lo + pix * p.res_ld + col : nullptr, r);
+#endif
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += r[j];
         }
