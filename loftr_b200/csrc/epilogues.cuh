@@ -998,10 +998,15 @@ struct EpiConv {
     const int c_lo = n0 + (epi_half() == 0 ? 0 : kChunksHalf0) * 32;
     const int c_hi = min(n0 + (epi_half() == 0 ? kChunksHalf0 : kChunks) * 32, s.N);
     if (p.res_hi) {
+      // every 128-byte line the row segment touches (pixel rows of 196 channels are 400 bytes apart: the segment
+      // seldom starts on a line boundary, stepping from its first byte would skip its last line)
       const long pix = (static_cast<long>(batch) * p.H_out + y) * p.W_out + x;
-      for (int c = c_lo; c < c_hi; c += 64) {
-        prefetch_l2(p.res_hi + pix * p.res_ld + c);
-        prefetch_l2(p.res_lo + pix * p.res_ld + c);
+      const uintptr_t b0 = reinterpret_cast<uintptr_t>(p.res_hi + pix * p.res_ld + c_lo);
+      const uintptr_t e0 = reinterpret_cast<uintptr_t>(p.res_hi + pix * p.res_ld + c_hi);
+      const uintptr_t dlo = reinterpret_cast<uintptr_t>(p.res_lo) - reinterpret_cast<uintptr_t>(p.res_hi);
+      for (uintptr_t a = b0 & ~uintptr_t(127); a < e0; a += 128) {
+        prefetch_l2(reinterpret_cast<const void*>(a));
+        prefetch_l2(reinterpret_cast<const void*>(a + dlo));
       }
     }
     if (kUpMode == 2 && p.up_hi) {
