@@ -124,47 +124,78 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """`nvidia-smi -lms 25` in the background for the whole run (its start-up alone can take longer than a short timed
+    region); `with sampler:` marks the timed region and summary() keeps the rows whose nvidia-smi timestamp falls
+    inside it (same wall clock as datetime.now())."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
-
-    def __enter__(self):
+        self.t0 = self.t1 = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "25", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            import atexit
+            atexit.register(self.stop)       # every rank: never leave the sampling loop behind
         except Exception:
             self.proc = None
-        return self
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def __enter__(self):
+        import datetime
+        self.t0 = datetime.datetime.now()
+        return self
+
     def __exit__(self, *a):
+        import datetime
+        self.t1 = datetime.datetime.now()
+
+    def stop(self):
         if self.proc:
+            time.sleep(0.1)   # let the rows of the last milliseconds arrive
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+            self.proc = None
+
+    @staticmethod
+    def _ts(text):
+        import datetime
+        return datetime.datetime.strptime(text, "%Y/%m/%d %H:%M:%S.%f")
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
+        self.stop()
+        inside, near = [], []
         for r in self.rows:
             try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                ts = self._ts(r[0])
+            except Exception:
+                continue
+            if self.t0 is not None and self.t0 <= ts <= self.t1:
+                inside.append(r)
+            elif self.t0 is not None and abs((ts - self.t1).total_seconds()) < 0.25:
+                near.append(r)
+        use, where = (inside, "timed region") if inside else (near, "within 0.25 s of the timed region")
+        sm, mx, reasons = [], 0, set()
+        for r in use:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "sampled": where, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -181,6 +212,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU port)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    clk = ClockSampler(local)                        # sampling from now on; the timed region is marked with `with clk:`
     torch.backends.cudnn.allow_tf32 = False          # only matters for --backbone torch (fp32 parity mode)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = True
@@ -376,7 +408,7 @@ def run_b200(args):
     # ---- device-resident throughput
     barrier()
     launches0 = lib.lb_launch_count()
-    with ClockSampler(local) as clk:
+    with clk:
         ms_steps = timed(lambda: main.step(), K)
         barrier()
     launches = lib.lb_launch_count() - launches0

@@ -16,6 +16,7 @@
 #include "epilogues.cuh"
 #include "gemm_split.cuh"
 #include "simt_kernels.cuh"
+#include "kv_gemm.cuh"
 #include "comm.cuh"
 #include "stem_tc.cuh"
 
@@ -709,7 +710,54 @@ static int lb::tf_layer_pass(const LbEncoderLayerWeights& lw, int C, int H, cons
       // 1-3 fused: k|v projection with the K^T V reduction in its epilogue, then the q projection
       // with the attention product in its epilogue; q, k, v never reach HBM.   [transformer.py:47-50, linear_attention.py:31-46]
       const int m_tiles_s = cdiv(s_group_rows, kBlockM);
-      {
+      // K^T V on the tensor cores (kv_gemm.cuh; LOFTR_B200_KV_GEMM=0: the CUDA-core reduction inside EpiKv)
+      static int kv_gemm = -1;
+      if (kv_gemm < 0) {
+        const char* e = getenv("LOFTR_B200_KV_GEMM");
+        kv_gemm = e ? (atoi(e) != 0 ? 1 : 0) : 1;
+      }
+      if (kv_gemm && use_tma_store() && C == 256 && H == 8) {
+        int sms = 0;
+        LB_TRY(device_check(&sms));
+        __half* kvp_hi = w.h_hi + s_base * ldc;   // the MLP hidden planes [R, 2C] are free at this point of the layer
+        __half* kvp_lo = w.h_lo + s_base * ldc;
+        {
+          using Epi = EpiKvProj<256>;
+          Planes A{cat_hi + s_base * ldc, cat_lo + s_base * ldc, ldc, static_cast<long>(s_group_rows) * ldc};
+          Planes B{lw.wkv_hi, lw.wkv_lo, C, 0};
+          typename Epi::Params ep;
+          ep.rowmask = mask ? mask + s_base : nullptr;
+          ep.acc_scale = lw.s_qkv;
+          LB_TRY(fill_out_maps(&ep.om, kvp_hi, kvp_lo, ldc, nullptr, 0, 2 * C, s_group_rows, n_groups_s));
+          LB_TRY((launch_gemm<256, Epi>(TAG_KV, A, B, n_groups_s, s_group_rows, 2 * C, C, 0, ep, stream)));
+        }
+        {
+          CUtensorMap tm_hi, tm_lo;
+          LB_TRY(make_map(&tm_hi, kvp_hi, 2 * C, s_group_rows, n_groups_s, ldc, static_cast<long>(s_group_rows) * ldc, 64, 64));
+          LB_TRY(make_map(&tm_lo, kvp_lo, 2 * C, s_group_rows, n_groups_s, ldc, static_cast<long>(s_group_rows) * ldc, 64, 64));
+          const int kb_total = cdiv(s_group_rows, 64);
+          const int parts_cap = m_tiles_s > kKvSplits ? m_tiles_s : kKvSplits;   // capacity of kv_part in 1056-float partials per (group, head)
+          int splits = sms / (2 * n_groups_s);
+          if (splits < 1) splits = 1;
+          if (splits > kb_total) splits = kb_total;
+          if (splits > parts_cap) splits = parts_cap;
+          const int kb_per = cdiv(kb_total, splits);
+          splits = cdiv(kb_total, kb_per);
+          static bool configured[kMaxDevices] = {false};
+          int dev = 0;
+          LB_CUDA(cudaGetDevice(&dev));
+          if (!configured[dev]) {
+            LB_CUDA(cudaFuncSetAttribute(kv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvGemmSmem));
+            configured[dev] = true;
+          }
+          KvGemmParams kp{w.kv_part, kb_total, kb_per, splits};
+          kv_gemm_kernel<<<dim3(splits, 2, n_groups_s), kKvGemmThreads, kKvGemmSmem, stream>>>(tm_hi, tm_lo, kp);
+          LB_LAUNCHED();
+          const long total = static_cast<long>(n_groups_s) * H * per;
+          kv_tile_merge_kernel<<<cdiv(total, 256), 256, 0, stream>>>(w.kv_part, splits, H * per, w.kv, total);
+          LB_LAUNCHED();
+        }
+      } else {
         using Epi = EpiKv<256, 32>;
         Planes A{cat_hi + s_base * ldc, cat_lo + s_base * ldc, ldc, static_cast<long>(s_group_rows) * ldc};
         Planes B{lw.wkv_hi, lw.wkv_lo, C, 0};

@@ -998,15 +998,12 @@ struct EpiConv {
     const int c_lo = n0 + (epi_half() == 0 ? 0 : kChunksHalf0) * 32;
     const int c_hi = min(n0 + (epi_half() == 0 ? kChunksHalf0 : kChunks) * 32, s.N);
     if (p.res_hi) {
-      // every 128-byte line the row segment touches (pixel rows of 196 channels are 400 bytes apart: the segment
-      // seldom starts on a line boundary, stepping from its first byte would skip its last line)
+      // one request per 128 bytes of the row segment from its first byte (measured: also covering the last, partially
+      // used line -- pixel rows of 196 channels are 400 bytes apart -- costs more than it saves: 635 -> 675 us)
       const long pix = (static_cast<long>(batch) * p.H_out + y) * p.W_out + x;
-      const uintptr_t b0 = reinterpret_cast<uintptr_t>(p.res_hi + pix * p.res_ld + c_lo);
-      const uintptr_t e0 = reinterpret_cast<uintptr_t>(p.res_hi + pix * p.res_ld + c_hi);
-      const uintptr_t dlo = reinterpret_cast<uintptr_t>(p.res_lo) - reinterpret_cast<uintptr_t>(p.res_hi);
-      for (uintptr_t a = b0 & ~uintptr_t(127); a < e0; a += 128) {
-        prefetch_l2(reinterpret_cast<const void*>(a));
-        prefetch_l2(reinterpret_cast<const void*>(a + dlo));
+      for (int c = c_lo; c < c_hi; c += 64) {
+        prefetch_l2(p.res_hi + pix * p.res_ld + c);
+        prefetch_l2(p.res_lo + pix * p.res_ld + c);
       }
     }
     if (kUpMode == 2 && p.up_hi) {
@@ -1213,6 +1210,52 @@ struct OpAddF { __device__ float operator()(float a, float b) const { return a +
 struct OpMaxU64 {
   __device__ unsigned long long operator()(unsigned long long a, unsigned long long b) const {
     return a > b ? a : b;
+  }
+};
+
+// EpiKvProj: epilogue of the k|v projection when K^T V runs on the tensor cores (kv_gemm.cuh).  Column layout of the
+// projection (weights permuted on the host, loftr.py): n-tile t = [K of heads 4t..4t+3 (128 columns) | V of the same
+// heads (128 columns)].  K = elu(k)+1 and V, both times the padding mask (linear_attention.py:32-39), are written as
+// fp16 hi/lo planes (TMA stores) -- the MN-major operands of kv_gemm_kernel.  Rows past the group's end are clipped by
+// the store map.
+template <int BLOCK_N>
+struct EpiKvProj {
+  static_assert(BLOCK_N == 256, "built for the coarse transformer (d_model 256, 8 heads)");
+  struct Params {
+    const uint8_t* rowmask;  // optional [batches*M] (1 = valid)
+    float acc_scale;
+    OutMaps om;              // planes [batches][M][512]
+  };
+  static constexpr int kSmemBytes = kEpiScratchBytes;
+  const Params& p;
+  const GemmShape& s;
+  uint32_t* scr;
+  __device__ EpiKvProj(const Params& p_, uint8_t* smem, const GemmShape& s_) : p(p_), s(s_), scr(epi_scratch(smem)) {}
+  __device__ void item_begin(int, int, int) {}
+  __device__ void item_end(int, int, int) {}
+  __device__ void prefetch(int, int, int) {}
+  __device__ void tile(uint32_t tmem_acc, int batch, int m0, int n0) {
+    const int r = m0 + epi_row();
+    const bool row_ok = r < s.M;
+    float mk = row_ok ? 1.f : 0.f;
+    if (row_ok && p.rowmask) mk = p.rowmask[static_cast<long>(batch) * s.M + r] ? 1.f : 0.f;
+    const bool is_k = epi_half() == 0;
+    const int quarter = (epi_tid() >> 5) & 3;
+    const int c_begin = epi_half() * 4;
+#pragma unroll 1
+    for (int c = c_begin; c < c_begin + 4; ++c) {
+      float x[32];
+      load_acc32(tmem_acc, c * 32, x);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] *= p.acc_scale;
+      if (is_k) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = x[j] > 0.f ? x[j] + 1.f : expf(x[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] *= mk;
+      warp_tma_store_planes32(scr, p.om, OutCoord{n0 + c * 32, m0 + quarter * 32, batch, 0}, x);
+    }
   }
 };
 
