@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "../../include/loftr_b200.h"
@@ -275,7 +276,7 @@ struct Planes {
 // in profiles/r1_kernel_variants_ab.md: the pair kernels win where the MMA phase dominates (convolutions -7 %,
 // mlp[0] -9 %, fine merge -8 %) and lose a little where the epilogue dominates (projections, score passes), so
 // they are used for exactly those launches.  LOFTR_B200_MODE=0|1|2 forces one mode for every launch.
-static int kernel_mode(int tag) {
+static int kernel_mode(int tag, int block_n = 0) {
   static int forced = -2;
   if (forced == -2) {
     const char* e = getenv("LOFTR_B200_MODE");
@@ -283,6 +284,32 @@ static int kernel_mode(int tag) {
     if (forced < -1 || forced > 2) forced = -1;
   }
   if (forced >= 0) return forced;
+  // per-kernel-kind override for A/B runs: LOFTR_B200_MODE_TAGS="merge_ln=2,mlp2_ln_res=2" (names of kTagNames)
+  static int per_tag[TAG_COUNT];
+  static bool parsed = false;
+  if (!parsed) {
+    for (int t = 0; t < TAG_COUNT; ++t) per_tag[t] = -1;
+    if (const char* e = getenv("LOFTR_B200_MODE_TAGS")) {
+      std::string spec(e);
+      size_t pos = 0;
+      while (pos < spec.size()) {
+        const size_t end = spec.find(',', pos);
+        const std::string item = spec.substr(pos, end == std::string::npos ? std::string::npos : end - pos);
+        const size_t eq = item.find('=');
+        if (eq != std::string::npos) {
+          for (int t = 0; t < TAG_COUNT; ++t)
+            if (item.substr(0, eq) == kTagNames[t]) per_tag[t] = atoi(item.c_str() + eq + 1);
+        }
+        if (end == std::string::npos) break;
+        pos = end + 1;
+      }
+    }
+    parsed = true;
+  }
+  if (tag >= 0 && tag < TAG_COUNT && per_tag[tag] >= 0 && per_tag[tag] <= 2) return per_tag[tag];
+  // the two LayerNorm GEMMs of the coarse transformer (N = 256, K = 256 / 512): with the pair's half-B stages the ring is
+  // three deep instead of two, 1172 -> 1105 us per step (profiles/r2u_*); the fine ones (N = 128) do not gain
+  if ((tag == TAG_MERGE_LN || tag == TAG_MLP2_LN) && block_n == 256) return 2;
   return (tag == TAG_CONV || tag == TAG_MLP1 || tag == TAG_FINE_MERGE) ? 2 : 0;
 }
 
@@ -390,7 +417,7 @@ static int launch_gemm(int tag, const Planes& A, const Planes& B, int batches, i
   s.n_chunks = (s.n_tiles + s.tiles_per_chunk - 1) / s.tiles_per_chunk;
   s.conv = ConvGeom{0, 0, 0, 0, 0, 0, 0, 0, 0};
 
-  const int mode = s.m_tiles >= 2 ? kernel_mode(tag) : 0;
+  const int mode = s.m_tiles >= 2 ? kernel_mode(tag, BN) : 0;
   const int cl = mode == 0 ? 1 : 2;
   GemmMaps mp;
   LB_TRY(make_map(&mp.a_hi, A.hi, K, M, batches, A.ld, A.batch_stride, kBlockM));
