@@ -377,8 +377,11 @@ def run_b200(args):
         # the GPUs idled (and dropped their clocks) while the communicators were being created: repeat the W warm-up
         # steps of the headline workload right before the timed region (measured at N = 2: 28.4 ms/step for the first
         # ten steps after the idle gap vs 24.8 ms afterwards, 1665 MHz vs 1965 MHz)
-        for _ in range(max(Wm, 8)):
+        # (r2w: eight steps were not always enough -- 28.05 ms/step timed right after them vs 22.5 ms a second later;
+        # the count is fixed, not time-based, so that every rank issues the same number of collectives)
+        for _ in range(max(Wm, 60)):
             main.step()
+        torch.cuda.synchronize()
         over_ranks(0.0)
         barrier()
         sys.stdout.flush()
