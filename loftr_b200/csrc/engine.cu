@@ -379,13 +379,23 @@ static int launch_raw(int tag, const GemmMaps& maps, const GemmShape& s, const t
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  static int pdl = -1;   // LOFTR_B200_PDL=1: programmatic dependent launch of the tensor-core kernels (gemm_split.cuh)
+  if (pdl < 0) {
+    const char* e = getenv("LOFTR_B200_PDL");
+    pdl = e ? (atoi(e) != 0 ? 1 : 0) : 0;
+  }
+  if (pdl) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   LB_CUDA(cudaLaunchKernelEx(&cfg, kern, maps.a_hi, maps.a_lo, maps.b_hi, maps.b_lo, maps.ar_hi, maps.ar_lo, maps.br_hi,
                              maps.br_lo, s, ep));
   LB_LAUNCHED();

@@ -133,3 +133,32 @@ def test_unsupported_shapes_fail_at_construction():
     cfg["fine_window_size"] = 7
     with pytest.raises(ValueError, match="fine windows"):
         loftr_b200.LoFTR(cfg)
+
+
+def test_bench_clock_sampler_filters_by_timestamp():
+    """bench.py's nvidia-smi sampler runs for the whole process; only rows stamped inside the timed region count
+    (rows within 0.25 s of its end are the fallback when the region was shorter than one sampling period)."""
+    import datetime
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    c = bench.ClockSampler.__new__(bench.ClockSampler)   # no nvidia-smi process
+    c.proc = None
+    now = datetime.datetime.now()
+    c.t0, c.t1 = now, now + datetime.timedelta(seconds=0.3)
+
+    def row(dt, clk, cap="Active"):
+        ts = (now + datetime.timedelta(seconds=dt)).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+        return [ts, str(clk), "1965", "800.1", "Not Active", "Not Active", "Not Active", cap]
+
+    c.rows = [row(-0.2, 1500), row(0.05, 1800), row(0.1, 1820), row(0.4, 1700, "Not Active")]
+    s = c.summary()
+    assert s["samples"] == 2 and s["sm_mhz"] == 1810.0 and s["sm_max_mhz"] == 1965.0
+    assert s["reasons"] == ["sw_power_cap"] and s["sampled"] == "timed region"
+    c.rows = [row(-0.6, 1500), row(0.4, 1700)]
+    s = c.summary()
+    assert s["samples"] == 1 and s["sm_mhz"] == 1700.0 and s["sampled"].startswith("within")
+    c.rows = [["garbage"], row(-3.0, 1000)]
+    assert c.summary()["samples"] == 0
