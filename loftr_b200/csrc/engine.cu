@@ -386,10 +386,13 @@ static int launch_raw(int tag, const GemmMaps& maps, const GemmShape& s, const t
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  static int pdl = -1;   // LOFTR_B200_PDL=1: programmatic dependent launch of the tensor-core kernels (gemm_split.cuh)
+  // programmatic dependent launch of the tensor-core kernels (gemm_split.cuh): the next kernel's set-up overlaps this
+  // one's tail.  LOFTR_B200_PDL=0 disables it (4 alternating A/B pairs: median 21.08 vs 21.25 ms/step,
+  // profiles/r2y_ab_pdl_alternating.txt)
+  static int pdl = -1;
   if (pdl < 0) {
     const char* e = getenv("LOFTR_B200_PDL");
-    pdl = e ? (atoi(e) != 0 ? 1 : 0) : 0;
+    pdl = e ? (atoi(e) != 0 ? 1 : 0) : 1;
   }
   if (pdl) {
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;

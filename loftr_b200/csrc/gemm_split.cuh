@@ -195,7 +195,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   if (kCluster > 1) cluster_sync_all();   // peer barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // Programmatic dependent launch (engine.cu sets the launch attribute when LOFTR_B200_PDL=1; without it both
+  // Programmatic dependent launch (engine.cu sets the launch attribute unless LOFTR_B200_PDL=0; without it both
   // instructions are no-ops): the NEXT kernel of the stream may be scheduled as soon as every CTA of this grid got
   // here -- its CTAs take over SMs as ours exit and run their own set-up (barriers, TMEM allocation, descriptor
   // prefetch) -- while everything below this line first waits until the PREVIOUS grid has completed and flushed.

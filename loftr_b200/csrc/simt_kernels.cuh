@@ -8,6 +8,11 @@
 
 namespace lb {
 
+// Programmatic dependent launch: lets a tensor-core kernel that follows on the stream (launched with the PDL attribute,
+// gemm_split.cuh) be scheduled and run its set-up while this grid is still working; it waits for this grid's completion
+// before it touches global memory.  A no-op when the next launch is an ordinary one.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 // fp32 [rows, cols] (ld_x) -> fp16 hi/lo planes (ld_pl, column offset col0).  Weight packing and tests.
 __global__ void split_planes_kernel(const float* __restrict__ x, long rows, int cols, int ld_x,
@@ -32,6 +37,7 @@ __global__ void split_planes_kernel(const float* __restrict__ x, long rows, int 
 __global__ void coarse_prep_kernel(const float* __restrict__ feat, int nhwc, const float* __restrict__ pe, int C,
                                    int h, int w, int pe_h, int pe_w, float* __restrict__ x_f32,
                                    __half* __restrict__ cat_hi, __half* __restrict__ cat_lo) {
+  pdl_trigger();
   __shared__ float tile[32][33];
   const int L = h * w;
   const int img = blockIdx.z;
@@ -252,6 +258,7 @@ __global__ void kv_merge_kernel(const float* __restrict__ part, int nsplit, int 
 // (fixed order over the row tiles: bit-reproducible).
 __global__ void kv_tile_merge_kernel(const float* __restrict__ part, int m_tiles, int hper, float* __restrict__ kv,
                                      long total) {
+  pdl_trigger();
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (i >= total) return;
   const long g = i / hper;
@@ -389,6 +396,7 @@ __global__ void __launch_bounds__(32 * H, 3) window_attn_kernel(const float* __r
                                                                 int rows_per_group, int n_groups, float eps,
                                                                 __half* __restrict__ att_hi, __half* __restrict__ att_lo,
                                                                 int ld_att) {
+  pdl_trigger();
   static_assert(D == 16 && H == 8, "fine head layout");
   constexpr int C = D * H;  // 128
   constexpr int PER = D * D + D;
@@ -509,6 +517,7 @@ __global__ void __launch_bounds__(32 * H, 3) window_attn_kernel(const float* __r
 __global__ void lse_merge_kernel(const float2* __restrict__ part, int nparts, long count, float base,
                                  const float* __restrict__ bin, const float* __restrict__ bin_pot, int per,
                                  const uint8_t* __restrict__ valid, float* __restrict__ out) {
+  pdl_trigger();
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (i >= count) return;
   const bool use_extra = bin != nullptr;
@@ -879,6 +888,7 @@ struct FineBiasParams {
   float* gbias;            // [2M, Cf]
 };
 __global__ void __launch_bounds__(128) fine_bias_kernel(const FineBiasParams p) {
+  pdl_trigger();
   __shared__ float s_fc[kFineBiasWin][256];
   __shared__ float s_c[kFineBiasWin][128];
   const long win0 = static_cast<long>(blockIdx.x) * kFineBiasWin;

@@ -39,6 +39,7 @@ __device__ __forceinline__ uint32_t stem_sw128(int row, int k) {   // byte offse
 }
 
 __global__ void __launch_bounds__(kStemThreads, 1) conv_stem7x7_tc_kernel(const __grid_constant__ StemTcParams p) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the first convolution may set up meanwhile
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) asm volatile("trap;");
   uint8_t* sA = smem;                                   // [buf][hi|lo][16 KB]
