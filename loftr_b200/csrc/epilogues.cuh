@@ -17,6 +17,14 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 // exp(x) for x <= 0 (softmax numerators)
 __device__ __forceinline__ float exp_fast(float x) { return ex2_approx(x * kLog2e); }
+// elu(x) + 1 = x + 1 (x > 0) | exp(x) (x <= 0): the feature map of the linear attention (linear_attention.py:7-8).
+// Branch-free: the exponential is always evaluated (ex2.approx of min(x, 0) * log2 e, relative error ~1e-6, the level
+// of the split-precision GEMMs around it) and selected.  expf() compiled to a guarded slow path per element and was
+// 25 % of the k|v projection kernel's samples (profiles/r3a_*).
+__device__ __forceinline__ float elu_plus1(float x) {
+  const float e = exp_fast(fminf(x, 0.f));
+  return x > 0.f ? x + 1.f : e;
+}
 
 __device__ __forceinline__ int epi_tid() { return threadIdx.x - kEpiWarp0 * 32; }   // 0..255
 __device__ __forceinline__ int epi_row() { return epi_tid() & 127; }                  // accumulator row (TMEM lane)
@@ -420,7 +428,7 @@ struct EpiActStore {
       for (int j = 0; j < 32; ++j) x[j] *= p.acc_scale;
       if (col < p.elu_cols) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = x[j] > 0.f ? x[j] + 1.f : expf(x[j]);
+        for (int j = 0; j < 32; ++j) x[j] = elu_plus1(x[j]);
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] *= mk;
@@ -492,7 +500,7 @@ struct EpiKv {
         for (int i = 0; i < 32; ++i) x[i] *= p.acc_scale;
         if (half == 0) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = x[i] > 0.f ? x[i] + 1.f : expf(x[i]);
+          for (int i = 0; i < 32; ++i) x[i] = elu_plus1(x[i]);
         }
         float* dst = (half == 0 ? sK : sV) + row * D;
 #pragma unroll
@@ -607,7 +615,7 @@ struct EpiAttn {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float x = q[j] * p.acc_scale;
-        q[j] = (x > 0.f ? x + 1.f : expf(x)) * mk;
+        q[j] = elu_plus1(x) * mk;
       }
       float zden = p.eps;
 #pragma unroll
@@ -1250,7 +1258,7 @@ struct EpiKvProj {
       for (int j = 0; j < 32; ++j) x[j] *= p.acc_scale;
       if (is_k) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = x[j] > 0.f ? x[j] + 1.f : expf(x[j]);
+        for (int j = 0; j < 32; ++j) x[j] = elu_plus1(x[j]);
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] *= mk;
