@@ -750,6 +750,14 @@ struct EpiLayerNorm {
     const float rstd = rsqrtf(var + p.eps);
 #pragma unroll 1
     for (int c = c_begin; c < c_end; ++c) {
+#if LB_COALESCE
+      // residual rows of this 32-column group: requested before the accumulator group is fetched and normalised
+      // (18 % of the mlp[2]+norm2 kernel's samples waited on them when they were loaded after the arithmetic)
+      uint4 rh[4], rl[4];
+      if (p.res_hi)
+        warp_issue_planes32(row_ok ? p.res_hi + grow * p.ld_res_pl + c * 32 : nullptr,
+                            row_ok ? p.res_lo + grow * p.ld_res_pl + c * 32 : nullptr, rh, rl);
+#endif
       float x[32];
       load_acc32(tmem_acc, c * 32, x);
 #pragma unroll
@@ -771,8 +779,12 @@ struct EpiLayerNorm {
       }
       if (p.res_hi) {
         float r[32];
+#if LB_COALESCE
+        warp_finish_planes32(scr, rh, rl, r);
+#else
         warp_load_planes32(scr, row_ok ? p.res_hi + grow * p.ld_res_pl + c * 32 : nullptr,
                            row_ok ? p.res_lo + grow * p.ld_res_pl + c * 32 : nullptr, r);
+#endif
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] += r[j];
       }
